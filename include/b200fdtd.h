@@ -1,0 +1,146 @@
+/* b200fdtd.h -- C ABI of the B200-native FDTD engine (libb200fdtd.so).
+ *
+ * This is the drop-in boundary for the ONE hot call under spinsphotonics/pjz:
+ *
+ *     fields = fdtdz_jax.fdtdz(epsilon=, dt=, source_field=, source_waveform=,
+ *                              source_position=, absorption_mask=, pml_kappa=, pml_sigma=,
+ *                              pml_alpha=, pml_widths=, output_steps=,
+ *                              use_reduced_precision=, launch_params=, offset=)
+ *                                            -- /root/reference/src/pjz/_field.py:254-269
+ *
+ * whose implementation is the un-vendored PyPI package fdtdz>=1.1.3
+ * (/root/reference/setup.py:26).  In the reference that python function binds a JAX primitive
+ * lowered to an XLA GPU custom call `void fn(cudaStream_t, void** buffers, const char* opaque,
+ * size_t opaque_len)`.  The entry points below are what that FFI binds instead:
+ *
+ *   b200fdtd_run            <- the custom call's body (device buffers, caller's stream)
+ *   b200fdtd_xla_custom_call<- the legacy XLA custom-call symbol itself (same ABI as fdtd-z's)
+ *   b200fdtd_run_host       <- convenience for hosts without a device-array type (NumPy)
+ *   b200fdtd_workspace_bytes / b200fdtd_output_bytes / b200fdtd_num_outputs
+ *                           <- shape/scratch inference the python wrapper needs
+ *
+ * Conventions: plain pointers and sizes only, no C++/torch/JAX types; every function returns
+ * 0 on success or a B200FDTD_E* code (never throws, never aborts); the message of the last
+ * failure on the calling thread is b200fdtd_last_error().  Buffers are owned by the caller.
+ * b200fdtd_run is asynchronous w.r.t. the host and ordered on the stream it is given; it is
+ * re-entrant per (device, stream) and keeps no global mutable state.
+ *
+ * All arrays are C-order (last index fastest, i.e. z fastest), float32:
+ *   epsilon          (3, xx, yy, zz)      permittivity of the sub-volume at `off_*`; the rest of
+ *                                          the (X, Y, Z) domain is edge-replicated
+ *   source_field     (2, 1, Y, Z) | (2, X, 1, Z) | (2, 2, X, Y, 1)     (source_axis 0 | 1 | 2)
+ *   source_waveform  (tt, 2)
+ *   absorption_mask  (3, X, Y)
+ *   pml_kappa/sigma/alpha (Z, 2)           column 0: integer-z nodes, column 1: z+1/2 nodes
+ *   output           (n_out, 3, xx, yy, zz) E after step n for n in range(out_start,out_stop,out_step)
+ */
+#ifndef B200FDTD_H_
+#define B200FDTD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FDTD_ABI_VERSION 1
+
+enum {
+  B200FDTD_OK = 0,
+  B200FDTD_EINVAL = 1,     /* bad descriptor / shapes / null pointer          */
+  B200FDTD_EWORKSPACE = 2, /* workspace too small                             */
+  B200FDTD_ECUDA = 3,      /* a CUDA call failed (see b200fdtd_last_error)    */
+  B200FDTD_EUNSUPPORTED = 4
+};
+
+/* Index of each device buffer in `inputs[]`. */
+enum {
+  B200FDTD_IN_EPSILON = 0,
+  B200FDTD_IN_SOURCE_FIELD = 1,
+  B200FDTD_IN_SOURCE_WAVEFORM = 2,
+  B200FDTD_IN_ABSORPTION_MASK = 3,
+  B200FDTD_IN_PML_KAPPA = 4,
+  B200FDTD_IN_PML_SIGMA = 5,
+  B200FDTD_IN_PML_ALPHA = 6,
+  B200FDTD_NUM_INPUTS = 7
+};
+
+/* Kernel selection (launch_params). */
+enum {
+  B200FDTD_KERNEL_AUTO = 0,
+  B200FDTD_KERNEL_TWOPASS = 1,  /* one H launch + one E launch per step, in place          */
+  B200FDTD_KERNEL_SYSTOLIC = 2  /* one persistent launch: fused H+E, x-sweep, L2-pipelined  */
+};
+
+/* Static description of one engine call (everything that is a python scalar/tuple at
+ * /root/reference/src/pjz/_field.py:254-269 plus the array shapes). */
+typedef struct b200fdtd_desc {
+  uint32_t struct_bytes;        /* = sizeof(b200fdtd_desc)                                  */
+  uint32_t abi_version;         /* = B200FDTD_ABI_VERSION                                   */
+  int32_t X, Y, Z;              /* full domain: absorption_mask.shape[1:], pml_*.shape[0]   */
+  int32_t xx, yy, zz;           /* epsilon.shape[1:]                                        */
+  int32_t off_x, off_y, off_z;  /* `offset`                                                 */
+  int32_t tt;                   /* source_waveform.shape[0] = number of time steps          */
+  int32_t source_axis;          /* 0 | 1 | 2, from source_field's shape                     */
+  int32_t source_position;      /* `source_position`                                        */
+  int32_t pml_lo, pml_hi;       /* `pml_widths`                                             */
+  int32_t out_start, out_stop, out_step; /* `output_steps`                                  */
+  int32_t use_reduced_precision;/* 1: E, H and dt/epsilon held as fp16, fp32 arithmetic     */
+  float dt;                     /* `dt`                                                     */
+  /* `launch_params` (all 0 = choose automatically) */
+  int32_t kernel;               /* B200FDTD_KERNEL_*                                        */
+  int32_t tile_y;               /* systolic: y-columns owned per CTA                        */
+  int32_t stages;               /* systolic: time steps in flight along the x sweep         */
+  int32_t threads;              /* CTA size override                                        */
+  int32_t reserved[4];
+} b200fdtd_desc;
+
+/* ABI version of the loaded library. */
+int b200fdtd_abi_version(void);
+
+/* Message for the last non-zero return on this thread ("" if none). */
+const char* b200fdtd_last_error(void);
+
+/* Validates `desc`; returns B200FDTD_OK or an error code. */
+int b200fdtd_validate(const b200fdtd_desc* desc);
+
+/* Number of snapshots len(range(out_start, out_stop, out_step)); < 0 on invalid desc. */
+int b200fdtd_num_outputs(const b200fdtd_desc* desc);
+
+/* Bytes of the output array (n_out, 3, xx, yy, zz) float32; 0 on invalid desc. */
+size_t b200fdtd_output_bytes(const b200fdtd_desc* desc);
+
+/* Scratch bytes b200fdtd_run needs in device memory; 0 on invalid desc. */
+size_t b200fdtd_workspace_bytes(const b200fdtd_desc* desc);
+
+/* The engine call.  `inputs[B200FDTD_NUM_INPUTS]` and `outputs[1]` are DEVICE pointers on the
+ * current device; `workspace` is device scratch of at least b200fdtd_workspace_bytes(desc)
+ * (256-byte aligned), or NULL to let the engine allocate/free it stream-ordered
+ * (cudaMallocAsync).  `stream` is a cudaStream_t passed as void*.  Returns immediately after
+ * enqueueing; errors raised later by the device surface at the caller's next sync. */
+int b200fdtd_run(const b200fdtd_desc* desc, const void* const* inputs, void* const* outputs,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers: allocates device memory on `device`, copies the inputs up,
+ * runs, copies the snapshots back, synchronises and frees.  For NumPy-style callers. */
+int b200fdtd_run_host(const b200fdtd_desc* desc, const void* const* host_inputs,
+                      void* const* host_outputs, int device);
+
+/* Legacy XLA GPU custom-call entry (the calling convention of fdtd-z's own custom call):
+ * buffers[0..6] = inputs in the order above, buffers[7] = output, buffers[8] = workspace
+ * (declared by the python wrapper as a second, scratch result); `opaque` = the bytes of a
+ * b200fdtd_desc.  Failures are reported through b200fdtd_last_error() and leave the output
+ * untouched (XLA's legacy API has no status channel). */
+void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
+                              size_t opaque_len);
+
+/* Introspection for tests/benchmarks: fills `info[8]` with what the AUTO policy would run for
+ * `desc` on the current device: {kernel, tile_y, stages, threads, ctas, smem_bytes,
+ * launches_per_run, l2_window_bytes>>20}.  */
+int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FDTD_H_ */

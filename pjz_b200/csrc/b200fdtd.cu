@@ -1,0 +1,462 @@
+// libb200fdtd.so -- C ABI (include/b200fdtd.h) and host-side driver of the B200 FDTD engine.
+//
+// Replaces the engine behind fdtdz_jax.fdtdz (/root/reference/src/pjz/_field.py:254-269; the
+// reference implementation is the absent PyPI package fdtdz>=1.1.3, /root/reference/setup.py:26).
+// Everything here is stream-ordered: coefficient preparation runs as small kernels on the
+// caller's stream, so b200fdtd_run never synchronises with the host.
+#include "../../include/b200fdtd.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "fdtd_common.cuh"
+#include "kernels_systolic.cuh"
+#include "kernels_twopass.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(B200FDTD_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int validate(const b200fdtd_desc* d) {
+  if (!d) return fail(B200FDTD_EINVAL, "desc is NULL");
+  if (d->struct_bytes != sizeof(b200fdtd_desc) || d->abi_version != B200FDTD_ABI_VERSION)
+    return fail(B200FDTD_EINVAL, "descriptor ABI mismatch (struct_bytes=%u, abi_version=%u)",
+                d->struct_bytes, d->abi_version);
+  if (d->X < 1 || d->Y < 1 || d->Z < 1)
+    return fail(B200FDTD_EINVAL, "domain must be positive, got (%d,%d,%d)", d->X, d->Y, d->Z);
+  if (d->xx < 1 || d->yy < 1 || d->zz < 1 || d->off_x < 0 || d->off_y < 0 || d->off_z < 0 ||
+      d->off_x + d->xx > d->X || d->off_y + d->yy > d->Y || d->off_z + d->zz > d->Z)
+    return fail(B200FDTD_EINVAL,
+                "epsilon sub-volume (%d,%d,%d) at offset (%d,%d,%d) does not fit domain (%d,%d,%d)",
+                d->xx, d->yy, d->zz, d->off_x, d->off_y, d->off_z, d->X, d->Y, d->Z);
+  if (d->tt < 0) return fail(B200FDTD_EINVAL, "tt must be >= 0");
+  if (d->source_axis < 0 || d->source_axis > 2)
+    return fail(B200FDTD_EINVAL, "source_axis must be 0, 1 or 2");
+  const int ext = d->source_axis == 0 ? d->X : (d->source_axis == 1 ? d->Y : d->Z);
+  if (d->source_position < 0 || d->source_position >= ext)
+    return fail(B200FDTD_EINVAL, "source_position %d outside [0,%d)", d->source_position, ext);
+  if (d->pml_lo < 0 || d->pml_hi < 0 || d->pml_lo + d->pml_hi > d->Z)
+    return fail(B200FDTD_EINVAL, "pml_widths (%d,%d) do not fit Z=%d", d->pml_lo, d->pml_hi, d->Z);
+  if (d->out_step < 1) return fail(B200FDTD_EINVAL, "output_steps step must be >= 1");
+  if (d->out_stop > d->out_start && (d->out_start < 0 || d->out_stop > d->tt + d->out_step - 1))
+    return fail(B200FDTD_EINVAL, "output_steps (%d,%d,%d) outside [0,tt=%d)", d->out_start,
+                d->out_stop, d->out_step, d->tt);
+  if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
+  if (d->kernel < 0 || d->kernel > 2) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  return B200FDTD_OK;
+}
+
+static int num_outputs(const b200fdtd_desc* d) {
+  if (d->out_stop <= d->out_start) return 0;
+  return (d->out_stop - d->out_start + d->out_step - 1) / d->out_step;
+}
+
+static Geom make_geom(const b200fdtd_desc* d) {
+  Geom g;
+  const int VW = d->use_reduced_precision ? 8 : 4;
+  g.X = d->X; g.Y = d->Y; g.Z = d->Z;
+  g.Zp = (d->Z + VW - 1) / VW * VW;
+  g.Zq = g.Zp / VW;
+  g.nlo = (d->pml_lo + VW - 1) / VW;
+  g.hi0 = d->pml_hi > 0 ? (d->Z - d->pml_hi) / VW : g.Zq;
+  if (g.hi0 < g.nlo) g.hi0 = g.nlo;
+  g.npg = g.nlo + (g.Zq - g.hi0);
+  g.xx = d->xx; g.yy = d->yy; g.zz = d->zz;
+  g.ox = d->off_x; g.oy = d->off_y; g.oz = d->off_z;
+  g.src_axis = d->source_axis; g.src_pos = d->source_position;
+  g.out_start = d->out_start; g.out_stop = d->out_stop; g.out_step = d->out_step;
+  g.tt = d->tt;
+  g.dt = d->dt;
+  g.P = (long long)g.Y * g.Zp;
+  g.N = (long long)g.X * g.P;
+  return g;
+}
+
+// ---- launch plan ---------------------------------------------------------------------------
+
+struct Plan {
+  int kernel;            // resolved B200FDTD_KERNEL_*
+  SystolicCfg sys;       // valid when kernel == SYSTOLIC
+};
+
+static int device_props(int* sms, int* l2_bytes) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(l2_bytes, cudaDevAttrL2CacheSize, dev));
+  return B200FDTD_OK;
+}
+
+template <typename T>
+static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
+  plan->kernel = d->kernel == B200FDTD_KERNEL_AUTO ? B200FDTD_KERNEL_SYSTOLIC : d->kernel;
+  if (plan->kernel == B200FDTD_KERNEL_SYSTOLIC) {
+    int sms = 0, l2 = 0;
+    int rc = device_props(&sms, &l2);
+    if (rc) return rc;
+    std::string why;
+    if (!systolic_configure<T>(g, d->tile_y, d->stages, d->threads, sms, l2, &plan->sys, &why)) {
+      if (d->kernel == B200FDTD_KERNEL_SYSTOLIC)
+        return fail(B200FDTD_EUNSUPPORTED, "systolic kernel unavailable: %s", why.c_str());
+      plan->kernel = B200FDTD_KERNEL_TWOPASS;
+    }
+  }
+  return B200FDTD_OK;
+}
+
+static int make_plan(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
+  return d->use_reduced_precision ? make_plan_t<__half>(d, g, plan) : make_plan_t<float>(d, g, plan);
+}
+
+// ---- workspace -----------------------------------------------------------------------------
+
+struct Workspace {
+  size_t fields;   // E[3], H[3]        (zeroed)
+  size_t fields2;  // E2[3], H2[3]      (zeroed; systolic only)
+  size_t psi;      // psiH[2], psiE[2]  (zeroed)
+  size_t sync;     // progress counters + status (zeroed)
+  size_t zero_end; // end of the zero-initialised prefix
+  size_t B, A, S, tab;
+  size_t total;
+};
+
+static Workspace carve(const Geom& g, bool reduced, bool systolic, const SystolicCfg* sys) {
+  Workspace w;
+  const size_t el = reduced ? 2 : 4;
+  const size_t VW = reduced ? 8 : 4;
+  size_t o = 0;
+  w.fields = o;  o = align_up(o + 6 * (size_t)g.N * el, 256);
+  w.fields2 = o; if (systolic) o = align_up(o + 6 * (size_t)g.N * el, 256);
+  w.psi = o;     o = align_up(o + (systolic ? 6 : 4) * (size_t)g.X * g.Y * g.npg * VW * sizeof(float), 256);
+  w.sync = o;    o = align_up(o + (systolic ? systolic_sync_bytes(*sys) : 0) + 256, 256);
+  w.zero_end = o;
+  w.B = o;       o = align_up(o + 3 * (size_t)g.N * el, 256);
+  w.A = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
+  w.S = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
+  w.tab = o;     o = align_up(o + 6 * (size_t)g.Zp * sizeof(float), 256);
+  w.total = o;
+  return w;
+}
+
+// ---- coefficient preparation kernels ------------------------------------------------------------
+
+// CPML tables, same double-precision formulas as oracle/fdtd_c.c:cpml_tables.
+__global__ void prep_tables_kernel(Geom g, const float* __restrict__ kappa,
+                                   const float* __restrict__ sigma,
+                                   const float* __restrict__ alpha, int pml_lo, int pml_hi,
+                                   float* __restrict__ tab) {
+  for (int z = blockIdx.x * blockDim.x + threadIdx.x; z < g.Zp; z += gridDim.x * blockDim.x) {
+    for (int col = 0; col < 2; ++col) {
+      float fa = 0.f, fb = 0.f, fik = 0.f;
+      if (z < g.Z) {
+        const double k = kappa[2 * z + col], s = sigma[2 * z + col], al = alpha[2 * z + col];
+        const double dt = (double)g.dt;
+        const double inv = isinf(k) ? 0.0 : 1.0 / k;
+        const double bb = exp(-(s * inv + al) * dt);
+        const bool in_pml = (z < pml_lo) || (z >= g.Z - pml_hi);
+        const double den = k * (s + k * al);
+        double aa = 0.0;
+        if (s != 0.0 && in_pml && isfinite(den) && den != 0.0) aa = s * (bb - 1.0) / den;
+        if (!isfinite(aa)) aa = 0.0;
+        fa = (float)aa; fb = (float)bb; fik = (float)inv;
+      }
+      tab[(3 * col + 0) * g.Zp + z] = fa;
+      tab[(3 * col + 1) * g.Zp + z] = fb;
+      tab[(3 * col + 2) * g.Zp + z] = fik;
+    }
+  }
+}
+
+__global__ void prep_absorber_kernel(Geom g, const float* __restrict__ mask,
+                                     float* __restrict__ A, float* __restrict__ S) {
+  const size_t n = 3 * (size_t)g.X * g.Y;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double s = mask[i], h = (double)g.dt / 2;
+    A[i] = (float)((1 - s * h) / (1 + s * h));
+    S[i] = (float)(1 / (1 + s * h));
+  }
+}
+
+// B_c = (dt / eps_c) * S_c with eps edge-replicated outside the sub-volume; 0 in the z padding.
+template <typename T>
+__global__ void prep_b_kernel(Geom g, const float* __restrict__ eps, const float* __restrict__ S,
+                              T* __restrict__ B) {
+  const size_t n = 3 * (size_t)g.N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % g.Zp);
+    size_t r = i / g.Zp;
+    const int y = (int)(r % g.Y); r /= g.Y;
+    const int x = (int)(r % g.X);
+    const int c = (int)(r / g.X);
+    float v = 0.f;
+    if (z < g.Z) {
+      int ex = x - g.ox; ex = ex < 0 ? 0 : (ex >= g.xx ? g.xx - 1 : ex);
+      int ey = y - g.oy; ey = ey < 0 ? 0 : (ey >= g.yy ? g.yy - 1 : ey);
+      int ez = z - g.oz; ez = ez < 0 ? 0 : (ez >= g.zz ? g.zz - 1 : ez);
+      const float e = eps[(((size_t)c * g.xx + ex) * g.yy + ey) * g.zz + ez];
+      const float s = S[((size_t)c * g.X + x) * g.Y + y];
+      v = __fmul_rn(__fdiv_rn(g.dt, e), s);
+    }
+    if constexpr (sizeof(T) == 4) B[i] = v;
+    else B[i] = __float2half_rn(v);
+  }
+}
+
+// ---- the run ----------------------------------------------------------------------------------
+
+template <typename T>
+static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, const Workspace& w,
+                     const void* const* in, void* const* out, char* ws, cudaStream_t st) {
+  constexpr int VW = VecTraits<T>::VW;
+  Ptrs<T> p;
+  T* fields = reinterpret_cast<T*>(ws + w.fields);
+  T* fields2 = reinterpret_cast<T*>(ws + w.fields2);
+  T* B = reinterpret_cast<T*>(ws + w.B);
+  float* psi = reinterpret_cast<float*>(ws + w.psi);
+  const size_t psi_n = (size_t)g.X * g.Y * g.npg * VW;
+  for (int c = 0; c < 3; ++c) {
+    p.E[c] = fields + (size_t)c * g.N;
+    p.H[c] = fields + (size_t)(3 + c) * g.N;
+    p.E2[c] = fields2 + (size_t)c * g.N;
+    p.H2[c] = fields2 + (size_t)(3 + c) * g.N;
+    p.B[c] = B + (size_t)c * g.N;
+  }
+  p.A = reinterpret_cast<float*>(ws + w.A);
+  p.tab = reinterpret_cast<float*>(ws + w.tab);
+  p.psiH[0] = psi; p.psiH[1] = psi + psi_n; p.psiE[0] = psi + 2 * psi_n; p.psiE[1] = psi + 3 * psi_n;
+  p.psiH2[0] = psi + 4 * psi_n; p.psiH2[1] = psi + 5 * psi_n;   // carved only for the systolic kernel
+  p.src = static_cast<const float*>(in[B200FDTD_IN_SOURCE_FIELD]);
+  p.wave = static_cast<const float*>(in[B200FDTD_IN_SOURCE_WAVEFORM]);
+  p.out = static_cast<float*>(out[0]);
+
+  CUDA_TRY(cudaMemsetAsync(ws, 0, w.zero_end, st));
+  float* S = reinterpret_cast<float*>(ws + w.S);
+  prep_tables_kernel<<<1, 256, 0, st>>>(
+      g, static_cast<const float*>(in[B200FDTD_IN_PML_KAPPA]),
+      static_cast<const float*>(in[B200FDTD_IN_PML_SIGMA]),
+      static_cast<const float*>(in[B200FDTD_IN_PML_ALPHA]), d->pml_lo, d->pml_hi,
+      const_cast<float*>(p.tab));
+  prep_absorber_kernel<<<256, 256, 0, st>>>(
+      g, static_cast<const float*>(in[B200FDTD_IN_ABSORPTION_MASK]), const_cast<float*>(p.A), S);
+  prep_b_kernel<T><<<148 * 8, 256, 0, st>>>(
+      g, static_cast<const float*>(in[B200FDTD_IN_EPSILON]), S, B);
+  CUDA_TRY(cudaGetLastError());
+
+  if (g.tt == 0) return B200FDTD_OK;
+  if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) {
+    int rc = systolic_launch<T>(g, p, plan.sys, reinterpret_cast<unsigned*>(ws + w.sync), st);
+    if (rc != 0)
+      return fail(B200FDTD_ECUDA, "systolic launch failed: %s",
+                  cudaGetErrorString((cudaError_t)rc));
+    return B200FDTD_OK;
+  }
+  const int per_plane = g.Y * g.Zq;
+  dim3 grid((per_plane + kTwoPassThreads - 1) / kTwoPassThreads, g.X);
+  for (int n = 0; n < g.tt; ++n) {
+    twopass_h_kernel<T><<<grid, kTwoPassThreads, 0, st>>>(g, p);
+    twopass_e_kernel<T><<<grid, kTwoPassThreads, 0, st>>>(g, p, n);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+static int run_impl(const b200fdtd_desc* d, const void* const* in, void* const* out, void* ws_in,
+                    size_t ws_bytes, cudaStream_t st) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!in || !out) return fail(B200FDTD_EINVAL, "inputs/outputs is NULL");
+  for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i)
+    if (!in[i]) return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i);
+  if (num_outputs(d) > 0 && !out[0]) return fail(B200FDTD_EINVAL, "outputs[0] is NULL");
+  const Geom g = make_geom(d);
+  if ((long long)g.Y * g.Zq > INT_MAX / 8) return fail(B200FDTD_EUNSUPPORTED, "plane too large");
+  if (g.X > 65535 && d->kernel == B200FDTD_KERNEL_TWOPASS)
+    return fail(B200FDTD_EUNSUPPORTED, "two-pass kernel supports X <= 65535");
+  Plan plan;
+  rc = make_plan(d, g, &plan);
+  if (rc) return rc;
+  if (plan.kernel == B200FDTD_KERNEL_TWOPASS && g.X > 65535)
+    return fail(B200FDTD_EUNSUPPORTED, "two-pass kernel supports X <= 65535");
+  const Workspace w = carve(g, d->use_reduced_precision != 0,
+                            plan.kernel == B200FDTD_KERNEL_SYSTOLIC, &plan.sys);
+  char* ws = static_cast<char*>(ws_in);
+  bool own = false;
+  if (!ws) {
+    CUDA_TRY(cudaMallocAsync((void**)&ws, w.total, st));
+    own = true;
+  } else {
+    if (ws_bytes < w.total)
+      return fail(B200FDTD_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+                  ws_bytes);
+    if ((uintptr_t)ws % 256 != 0) return fail(B200FDTD_EINVAL, "workspace must be 256-byte aligned");
+  }
+  rc = d->use_reduced_precision ? run_typed<__half>(d, g, plan, w, in, out, ws, st)
+                                : run_typed<float>(d, g, plan, w, in, out, ws, st);
+  if (own) cudaFreeAsync(ws, st);
+  return rc;
+}
+
+}  // namespace b200
+
+// ---- C ABI --------------------------------------------------------------------------------------
+
+using namespace b200;
+
+extern "C" {
+
+int b200fdtd_abi_version(void) { return B200FDTD_ABI_VERSION; }
+
+const char* b200fdtd_last_error(void) { return g_last_error.c_str(); }
+
+int b200fdtd_validate(const b200fdtd_desc* desc) { return validate(desc); }
+
+int b200fdtd_num_outputs(const b200fdtd_desc* desc) {
+  if (validate(desc)) return -1;
+  return num_outputs(desc);
+}
+
+size_t b200fdtd_output_bytes(const b200fdtd_desc* desc) {
+  if (validate(desc)) return 0;
+  return (size_t)num_outputs(desc) * 3 * desc->xx * desc->yy * desc->zz * sizeof(float);
+}
+
+size_t b200fdtd_workspace_bytes(const b200fdtd_desc* desc) {
+  if (validate(desc)) return 0;
+  const Geom g = make_geom(desc);
+  Plan plan;
+  if (make_plan(desc, g, &plan)) return 0;
+  return carve(g, desc->use_reduced_precision != 0, plan.kernel == B200FDTD_KERNEL_SYSTOLIC,
+               &plan.sys).total;
+}
+
+int b200fdtd_run(const b200fdtd_desc* desc, const void* const* inputs, void* const* outputs,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  return run_impl(desc, inputs, outputs, workspace, workspace_bytes,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* const* hout,
+                      int device) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (!hin || !hout) return fail(B200FDTD_EINVAL, "inputs/outputs is NULL");
+  CUDA_TRY(cudaSetDevice(device));
+  const size_t XY = (size_t)d->X * d->Y;
+  size_t bytes[B200FDTD_NUM_INPUTS];
+  bytes[B200FDTD_IN_EPSILON] = 3 * (size_t)d->xx * d->yy * d->zz * 4;
+  bytes[B200FDTD_IN_SOURCE_FIELD] =
+      (d->source_axis == 0 ? 2 * (size_t)d->Y * d->Z
+                           : d->source_axis == 1 ? 2 * (size_t)d->X * d->Z : 4 * XY) * 4;
+  bytes[B200FDTD_IN_SOURCE_WAVEFORM] = 2 * (size_t)(d->tt > 0 ? d->tt : 1) * 4;
+  bytes[B200FDTD_IN_ABSORPTION_MASK] = 3 * XY * 4;
+  bytes[B200FDTD_IN_PML_KAPPA] = bytes[B200FDTD_IN_PML_SIGMA] = bytes[B200FDTD_IN_PML_ALPHA] =
+      2 * (size_t)d->Z * 4;
+  const size_t out_bytes = b200fdtd_output_bytes(d);
+  const size_t ws_bytes = b200fdtd_workspace_bytes(d);
+  if (ws_bytes == 0) return B200FDTD_EINVAL;
+  cudaStream_t st = nullptr;
+  void* din[B200FDTD_NUM_INPUTS] = {nullptr};
+  void* dout[1] = {nullptr};
+  void* ws = nullptr;
+  rc = B200FDTD_OK;
+  auto cleanup = [&]() {
+    for (auto p : din) if (p) cudaFree(p);
+    if (dout[0]) cudaFree(dout[0]);
+    if (ws) cudaFree(ws);
+    if (st) cudaStreamDestroy(st);
+  };
+#define TRY_CLEAN(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      cleanup();                                                                            \
+      return fail(B200FDTD_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));          \
+    }                                                                                       \
+  } while (0)
+  TRY_CLEAN(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i) {
+    if (!hin[i]) { cleanup(); return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i); }
+    TRY_CLEAN(cudaMalloc(&din[i], bytes[i]));
+    TRY_CLEAN(cudaMemcpyAsync(din[i], hin[i], d->tt > 0 || i != B200FDTD_IN_SOURCE_WAVEFORM
+                                                  ? bytes[i] : 0,
+                              cudaMemcpyHostToDevice, st));
+  }
+  TRY_CLEAN(cudaMalloc(&dout[0], out_bytes ? out_bytes : 4));
+  TRY_CLEAN(cudaMalloc(&ws, ws_bytes));
+  rc = run_impl(d, din, dout, ws, ws_bytes, st);
+  if (rc == B200FDTD_OK && out_bytes) {
+    if (!hout[0]) { cleanup(); return fail(B200FDTD_EINVAL, "outputs[0] is NULL"); }
+    TRY_CLEAN(cudaMemcpyAsync(hout[0], dout[0], out_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  TRY_CLEAN(cudaStreamSynchronize(st));
+#undef TRY_CLEAN
+  cleanup();
+  return rc;
+}
+
+void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
+                              size_t opaque_len) {
+  if (!buffers || !opaque || opaque_len != sizeof(b200fdtd_desc)) {
+    fail(B200FDTD_EINVAL, "custom call: opaque must be a b200fdtd_desc (%zu bytes), got %zu",
+         sizeof(b200fdtd_desc), opaque_len);
+    return;
+  }
+  b200fdtd_desc d;
+  memcpy(&d, opaque, sizeof d);
+  void* outs[1] = {buffers[B200FDTD_NUM_INPUTS]};
+  const size_t ws_bytes = b200fdtd_workspace_bytes(&d);
+  run_impl(&d, const_cast<const void* const*>(buffers), outs, buffers[B200FDTD_NUM_INPUTS + 1],
+           ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!info) return fail(B200FDTD_EINVAL, "info is NULL");
+  const Geom g = make_geom(desc);
+  Plan plan;
+  rc = make_plan(desc, g, &plan);
+  if (rc) return rc;
+  memset(info, 0, 8 * sizeof(int64_t));
+  info[0] = plan.kernel;
+  if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) {
+    info[1] = plan.sys.tile_y; info[2] = plan.sys.stages; info[3] = plan.sys.threads;
+    info[4] = (int64_t)plan.sys.stages * plan.sys.ntiles; info[5] = plan.sys.smem_bytes;
+    info[6] = 1; info[7] = plan.sys.l2_window_bytes >> 20;
+  } else {
+    info[3] = kTwoPassThreads;
+    info[4] = (int64_t)((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads) * g.X;
+    info[6] = 2LL * g.tt;
+  }
+  return B200FDTD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""Drop-in for the ``fdtdz_jax`` module that pjz imports (/root/reference/src/pjz/_field.py:6).
+
+``fdtdz(...)`` keeps the keyword signature of the one call pjz makes
+(/root/reference/src/pjz/_field.py:254-269) and forwards it to ``libb200fdtd.so`` through
+the C ABI declared in ``include/b200fdtd.h``.  There is NO CPU fallback: without the built
+library or without a CUDA device the call raises.
+
+Array arguments may be torch tensors (CUDA tensors are used in place, zero-copy, on torch's
+current stream and the result is a CUDA tensor) or anything ``np.asarray`` accepts (host path:
+``b200fdtd_run_host`` copies up, runs, copies the snapshots back; the result is a NumPy array).
+
+``launch_params`` (opaque in pjz, ``SimParams.launch_params`` :53) may be ``None`` or a dict with
+any of ``kernel`` ("auto" | "twopass" | "systolic"), ``tile_y``, ``stages``, ``threads``.
+To make ``import fdtdz_jax`` resolve to this module: ``pjz_b200.fdtdz_jax.install()``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200fdtd.so")
+
+NUM_INPUTS = 7
+_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2}
+ABI_VERSION = 1
+
+
+class Desc(ctypes.Structure):
+  """``b200fdtd_desc`` (include/b200fdtd.h)."""
+  _fields_ = ([("struct_bytes", ctypes.c_uint32), ("abi_version", ctypes.c_uint32)] +
+              [(n, ctypes.c_int32) for n in (
+                  "X", "Y", "Z", "xx", "yy", "zz", "off_x", "off_y", "off_z", "tt",
+                  "source_axis", "source_position", "pml_lo", "pml_hi", "out_start",
+                  "out_stop", "out_step", "use_reduced_precision")] +
+              [("dt", ctypes.c_float)] +
+              [(n, ctypes.c_int32) for n in ("kernel", "tile_y", "stages", "threads")] +
+              [("reserved", ctypes.c_int32 * 4)])
+
+
+_lib = None
+
+
+def lib():
+  """The loaded C-ABI library; raises if it has not been built."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(
+          f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+          f"g.build()'` (there is no CPU fallback for the FDTD engine).")
+    L = ctypes.CDLL(LIB_PATH)
+    L.b200fdtd_abi_version.restype = ctypes.c_int
+    L.b200fdtd_last_error.restype = ctypes.c_char_p
+    L.b200fdtd_validate.restype = ctypes.c_int
+    L.b200fdtd_num_outputs.restype = ctypes.c_int
+    L.b200fdtd_output_bytes.restype = ctypes.c_size_t
+    L.b200fdtd_workspace_bytes.restype = ctypes.c_size_t
+    L.b200fdtd_run.restype = ctypes.c_int
+    L.b200fdtd_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.b200fdtd_run_host.restype = ctypes.c_int
+    L.b200fdtd_run_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_int]
+    L.b200fdtd_plan_info.restype = ctypes.c_int
+    if L.b200fdtd_abi_version() != ABI_VERSION:
+      raise RuntimeError("libb200fdtd.so ABI version mismatch")
+    _lib = L
+  return _lib
+
+
+def _last_error():
+  return lib().b200fdtd_last_error().decode("utf-8", "replace")
+
+
+def _is_torch(a):
+  return type(a).__module__.split(".")[0] == "torch"
+
+
+def _shape(a):
+  return tuple(int(s) for s in a.shape)
+
+
+def make_desc(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
+              pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
+              use_reduced_precision, launch_params, offset):
+  """Shape-checks the arguments the way the reference wrapper would and fills the descriptor."""
+  es, ss, ws, ms = (_shape(a) for a in (epsilon, source_field, source_waveform,
+                                         absorption_mask))
+  ks, gs, als = (_shape(a) for a in (pml_kappa, pml_sigma, pml_alpha))
+  if len(es) != 4 or es[0] != 3:
+    raise ValueError(f"epsilon must have shape (3, xx, yy, zz), got {es}")
+  if len(ms) != 3 or ms[0] != 3:
+    raise ValueError(f"absorption_mask must have shape (3, X, Y), got {ms}")
+  if len(ks) != 2 or ks[1] != 2 or gs != ks or als != ks:
+    raise ValueError(f"pml_kappa/sigma/alpha must share shape (Z, 2), got {ks}, {gs}, {als}")
+  if len(ws) != 2 or ws[1] != 2:
+    raise ValueError(f"source_waveform must have shape (tt, 2), got {ws}")
+  X, Y, Z = ms[1], ms[2], ks[0]
+  if len(ss) == 5 and ss == (2, 2, X, Y, 1):
+    axis = 2
+  elif len(ss) == 4 and ss == (2, 1, Y, Z):
+    axis = 0
+  elif len(ss) == 4 and ss == (2, X, 1, Z):
+    axis = 1
+  else:
+    raise ValueError(
+        f"source_field must have shape (2, 1, {Y}, {Z}), (2, {X}, 1, {Z}) or "
+        f"(2, 2, {X}, {Y}, 1), got {ss}")
+  if len(pml_widths) != 2 or len(output_steps) != 3 or len(offset) != 3:
+    raise ValueError("pml_widths, output_steps, offset must have 2, 3, 3 entries")
+  d = Desc()
+  d.struct_bytes, d.abi_version = ctypes.sizeof(Desc), ABI_VERSION
+  d.X, d.Y, d.Z = X, Y, Z
+  d.xx, d.yy, d.zz = es[1:]
+  d.off_x, d.off_y, d.off_z = (int(o) for o in offset)
+  d.tt = ws[0]
+  d.source_axis, d.source_position = axis, int(source_position)
+  d.pml_lo, d.pml_hi = int(pml_widths[0]), int(pml_widths[1])
+  d.out_start, d.out_stop, d.out_step = (int(v) for v in output_steps)
+  d.use_reduced_precision = int(bool(use_reduced_precision))
+  d.dt = float(dt)
+  lp = launch_params or {}
+  if not isinstance(lp, dict):
+    raise ValueError("launch_params must be None or a dict (kernel, tile_y, stages, threads)")
+  unknown = set(lp) - {"kernel", "tile_y", "stages", "threads"}
+  if unknown:
+    raise ValueError(f"unknown launch_params keys {sorted(unknown)}")
+  k = lp.get("kernel", "auto")
+  if k not in _KERNELS:
+    raise ValueError(f"launch_params['kernel'] must be one of {sorted(_KERNELS)}, got {k!r}")
+  d.kernel = _KERNELS[k]
+  d.tile_y, d.stages, d.threads = (int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads"))
+  rc = lib().b200fdtd_validate(ctypes.byref(d))
+  if rc != 0:
+    raise ValueError(_last_error())
+  return d
+
+
+def _void_array(ptrs):
+  arr = (ctypes.c_void_p * len(ptrs))()
+  for i, p in enumerate(ptrs):
+    arr[i] = p
+  return arr
+
+
+def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
+          pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps, use_reduced_precision,
+          launch_params=None, offset=(0, 0, 0)):
+  """Execute an FDTD simulation; signature of ``fdtdz_jax.fdtdz`` as called at
+  /root/reference/src/pjz/_field.py:254-269.  Returns ``(n_out, 3, xx, yy, zz)`` float32 E
+  snapshots for the steps ``range(*output_steps)``."""
+  arrays = [epsilon, source_field, source_waveform, absorption_mask, pml_kappa, pml_sigma,
+            pml_alpha]
+  d = make_desc(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
+                pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
+                use_reduced_precision, launch_params, offset)
+  L = lib()
+  nout = L.b200fdtd_num_outputs(ctypes.byref(d))
+  out_shape = (nout, 3, d.xx, d.yy, d.zz)
+  cuda_dev = None
+  for a in arrays:
+    if _is_torch(a) and a.is_cuda:
+      cuda_dev = a.device
+      break
+
+  if cuda_dev is None:
+    # Host path (NumPy in, NumPy out).
+    host = [np.ascontiguousarray(a.detach().cpu().numpy() if _is_torch(a) else np.asarray(a),
+                                 dtype=np.float32) for a in arrays]
+    out = np.empty(out_shape, np.float32)
+    import torch  # only to pick the device the caller selected
+    if not torch.cuda.is_available():
+      raise RuntimeError("fdtdz needs a CUDA device (no CPU fallback)")
+    rc = L.b200fdtd_run_host(ctypes.byref(d), _void_array([h.ctypes.data for h in host]),
+                             _void_array([out.ctypes.data]), torch.cuda.current_device())
+    if rc != 0:
+      raise RuntimeError(f"b200fdtd_run_host failed ({rc}): {_last_error()}")
+    return out
+
+  import torch
+  with torch.cuda.device(cuda_dev):
+    dev = [torch.as_tensor(a, dtype=torch.float32, device=cuda_dev).contiguous()
+           if _is_torch(a) else
+           torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda_dev)
+           for a in arrays]
+    ws_bytes = L.b200fdtd_workspace_bytes(ctypes.byref(d))
+    if ws_bytes == 0:
+      raise RuntimeError(f"b200fdtd_workspace_bytes failed: {_last_error()}")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda_dev)
+    out = torch.empty(out_shape, dtype=torch.float32, device=cuda_dev)
+    stream = torch.cuda.current_stream(cuda_dev).cuda_stream
+    rc = L.b200fdtd_run(ctypes.byref(d), _void_array([t.data_ptr() for t in dev]),
+                        _void_array([out.data_ptr()]), ws.data_ptr(), ws_bytes, stream)
+    if rc != 0:
+      raise RuntimeError(f"b200fdtd_run failed ({rc}): {_last_error()}")
+    # ws/dev are released to torch's caching allocator, which is stream-ordered.
+    return out
+
+
+def plan_info(**kwargs):
+  """What the engine would launch for these arguments (kernel, tiling, CTAs ...)."""
+  d = make_desc(**kwargs)
+  info = (ctypes.c_int64 * 8)()
+  rc = lib().b200fdtd_plan_info(ctypes.byref(d), info)
+  if rc != 0:
+    raise RuntimeError(_last_error())
+  names = ("kernel", "tile_y", "stages", "threads", "ctas", "smem_bytes", "launches_per_run",
+           "l2_window_mib")
+  out = dict(zip(names, (int(v) for v in info)))
+  out["kernel"] = {v: k for k, v in _KERNELS.items()}[out["kernel"]]
+  return out
+
+
+def install():
+  """Register this module as ``fdtdz_jax`` so that pjz's ``import fdtdz_jax`` binds to it."""
+  sys.modules["fdtdz_jax"] = sys.modules[__name__]
