@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Headline benchmark: FDTD Gcell-updates/s on BASELINE.json's configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, host cores)
+
+A "step" is ONE engine call: the full time-stepping of the workload (cfg2 at N=1: 90-degree
+bend, 256x256x128 total grid, 20 000 FDTD steps, fp32) through the C ABI.
+  value  : whole-job Gcell-updates/s, inputs resident in HBM, CUDA events, max over ranks.
+  e2e    : same metric through `pjz_b200.fdtdz_jax.fdtdz` with HOST (pinned) buffers --
+           host->device copies of every input and device->host copy of the snapshots inside
+           the timed region.
+  roofline: 60 B (fp32) per cell-update against the measured HBM copy peak.
+For N > 1 (torchrun) every rank runs an independent engine call of the same workload with its
+own source port -- the port/frequency batch axis of SURVEY.md 8(e); no data-path collective
+("scaling": "weak").
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fdtd_cell_updates_per_s"
+UNIT = "Gcell-updates/s"
+BYTES_PER_CELL = {False: 60.0, True: 30.0}
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--workload", default="bend", choices=["bend", "waveguide", "demux", "coupler"])
+  ap.add_argument("--tt", type=int, default=0, help="override the number of FDTD steps")
+  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic"])
+  ap.add_argument("--tile-y", type=int, default=0)
+  ap.add_argument("--stages", type=int, default=0)
+  ap.add_argument("--threads", type=int, default=0)
+  ap.add_argument("--reduced", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  return ap.parse_args()
+
+
+def make_workload(args, rank):
+  """Engine kwargs (NumPy, host) for the chosen BASELINE configuration."""
+  from pjz_b200 import _field as glue
+  from pjz_b200 import workloads as W
+  if args.workload == "bend":
+    eps, ports, params, omega = W.bend(reduced=args.reduced)
+    name = "cfg2 90-degree bend 256x256x128 total grid, 20000 steps"
+  elif args.workload == "waveguide":
+    eps, ports, params, omega = W.straight_waveguide(reduced=args.reduced)
+    name = "cfg1 straight waveguide 96x96x80 total grid, 4000 steps"
+  elif args.workload == "demux":
+    eps, ports, params, omega = W.demux(reduced=args.reduced)
+    name = "cfg3 demux 512x512x128 total grid, 20000 steps, 4 frequencies"
+  else:
+    eps, ports, params, omega, _ = W.coupler(reduced=args.reduced)
+    name = "cfg4 coupler 384x256x128 total grid, 20000 steps, one port per GPU"
+  if args.tt:
+    params = params._replace(tt=args.tt)
+    name += f" (tt overridden to {args.tt})"
+  lp = {"kernel": args.kernel}
+  for k, v in (("tile_y", args.tile_y), ("stages", args.stages), ("threads", args.threads)):
+    if v:
+      lp[k] = v
+  params = params._replace(launch_params=lp)
+  axis, pos, _ = ports[rank % len(ports)]
+  src = W.gaussian_port_source(eps, axis, pos)
+  kw, _, _ = glue.engine_inputs(eps, src, omega, pos, params)
+  host = {}
+  for k, v in kw.items():
+    host[k] = v.numpy() if hasattr(v, "numpy") else v
+  X, Y = host["absorption_mask"].shape[1:]
+  Z = host["pml_kappa"].shape[0]
+  return host, (X, Y, Z), params.tt, name
+
+
+ARRAYS = ("epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa",
+          "pml_sigma", "pml_alpha")
+
+
+class ClockSampler:
+  """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    try:
+      self.p = subprocess.Popen(
+          ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+           "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+    except OSError:
+      self.p = None
+
+  def stop(self):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if self.p is None:
+      return out
+    self.p.terminate()
+    try:
+      self.p.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.p.kill()
+    self.f.flush()
+    self.f.seek(0)
+    sm, mx, power, reasons = [], [], [], set()
+    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    for line in self.f.read().splitlines():
+      c = [v.strip() for v in line.split(",")]
+      if len(c) < 9:
+        continue
+      try:
+        sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+      except ValueError:
+        continue
+      for n, v in zip(names, c[5:9]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    os.unlink(self.f.name)
+    if sm:
+      out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm),
+                 power_w_max=max(power), reasons=sorted(reasons))
+    return out
+
+
+def measured_peak():
+  try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  except Exception:
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+  """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+  try:
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+      return json.load(f)
+  except Exception:
+    return None
+
+
+def cpu_sample(host, dims, seconds, reduced):
+  """Oracle port (C, OpenMP, all host threads) on a bounded sample of the SAME workload:
+  the same domain and inputs, the first n time steps; set-up time removed by differencing."""
+  from oracle import fdtd_c
+  cells = dims[0] * dims[1] * dims[2]
+  kw = dict(host)
+  kw["launch_params"] = None
+
+  def timed(n):
+    t0 = time.perf_counter()
+    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False)
+    return time.perf_counter() - t0
+
+  t_setup = timed(0)
+  n1 = 4
+  t1 = timed(n1)
+  rate = cells * n1 / max(t1 - t_setup, 1e-6)
+  n2 = int(max(8, min(host["source_waveform"].shape[0], seconds * rate / cells)))
+  t2 = timed(n2)
+  value = cells * n2 / max(t2 - t_setup, 1e-6) / 1e9
+  return {"value": value, "unit": UNIT, "cores": fdtd_c.max_threads(), "kind": "port",
+          "sample": f"same workload, first {n2} of {host['source_waveform'].shape[0]} FDTD steps "
+                    f"({t2 - t_setup:.1f} s of CPU work, set-up excluded), fp"
+                    f"{'16-storage' if reduced else '32'} C oracle with OpenMP"}
+
+
+def run_reference(args, rank, world):
+  """CPU arm: the oracle port (the engine's source is not in /root/reference -- SURVEY.md 8c),
+  all host threads, same config/metric; each step is a bounded sample of the workload."""
+  if rank != 0:
+    return
+  from oracle import fdtd_c
+  host, dims, tt, name = make_workload(args, 0)
+  cells = dims[0] * dims[1] * dims[2]
+  kw = dict(host)
+  kw["launch_params"] = None
+  t0 = time.perf_counter()
+  fdtd_c.fdtdz(**kw, steps_override=0, want_output=False)
+  t_setup = time.perf_counter() - t0
+  n = 24
+  for _ in range(args.warmup):
+    fdtd_c.fdtdz(**kw, steps_override=4, want_output=False)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False)
+  dt = time.perf_counter() - t0 - args.steps * t_setup
+  value = cells * n * args.steps / max(dt, 1e-9) / 1e9
+  cores = fdtd_c.max_threads()
+  sample = f"each step = first {n} of {tt} FDTD steps of the same workload; set-up excluded"
+  print(json.dumps({
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f16-storage/f32-math" if args.reduced else "f32", "data": "synthetic",
+      "config": {"workload": name, "grid": list(dims), "fdtd_steps": tt},
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }))
+
+
+def main():
+  args = parse()
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if args.impl == "reference":
+    run_reference(args, rank, world)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from pjz_b200 import fdtdz_jax
+  fdtdz_jax.lib()                      # fail loudly if the CUDA library is missing
+  assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+  torch.cuda.set_device(local)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+  host, dims, tt, name = make_workload(args, rank)
+  cells = dims[0] * dims[1] * dims[2]
+  dev = dict(host)
+  for k in ARRAYS:
+    dev[k] = torch.from_numpy(np.ascontiguousarray(host[k], np.float32)).cuda()
+  info = fdtdz_jax.plan_info(**dev)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- value: inputs resident in HBM ----------------------------------------------------------
+  for _ in range(args.warmup):
+    out = fdtdz_jax.fdtdz(**dev)
+  barrier()
+  sampler = ClockSampler(local) if rank == 0 else None
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for _ in range(args.steps):
+    out = fdtdz_jax.fdtdz(**dev)
+  ev1.record()
+  barrier()
+  ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  ms = float(ms.item())
+  clocks = sampler.stop() if sampler else None
+  checksum = float(out.double().abs().sum().item())
+  assert np.isfinite(checksum) and checksum > 0, "engine produced an empty/non-finite field"
+  value = world * cells * tt * args.steps / (ms / 1e3) / 1e9
+
+  # ---- e2e: HOST pinned buffers through the public call (copies inside the timed region) ----
+  e2e = None
+  if not args.no_e2e:
+    pinned = dict(host)
+    for k in ARRAYS:
+      t = torch.from_numpy(np.ascontiguousarray(host[k], np.float32)).pin_memory()
+      pinned[k] = t.numpy()
+    h2d = sum(pinned[k].nbytes for k in ARRAYS)
+    res = fdtdz_jax.fdtdz(**pinned)    # warm-up (also first-touch of the host path)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+      res = fdtdz_jax.fdtdz(**pinned)  # NumPy in -> b200fdtd_run_host -> NumPy out (synchronous)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+      dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * cells * tt * args.steps / float(t_e2e.item()) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes)}
+    assert np.isfinite(res).all()
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- roofline of the dominant kernel -----------------------------------------------------------
+  peak, peak_src = measured_peak()
+  bpc = BYTES_PER_CELL[bool(args.reduced)]
+  per_gpu = value / world
+  achieved = per_gpu * bpc                       # GB/s of ALGORITHMIC traffic
+  traffic = ncu_traffic()
+  if info["kernel"] == "systolic":
+    dominant = "systolic_kernel (1 launch per engine call; duration = call time incl. 3 prep kernels)"
+    launches = (3 + 2) * args.steps
+  else:
+    dominant = "twopass_h_kernel + twopass_e_kernel (2 launches per FDTD step)"
+    launches = (3 + 2 * tt) * args.steps
+  roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+              "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+              "kernel": dominant, "peak_source": peak_src,
+              "algorithmic_bytes_per_launch": bpc * cells * (tt if info["kernel"] == "systolic" else 0.5),
+              "bytes_per_cell_update": bpc}
+
+  cpu = None
+  if world == 1 and not args.no_cpu:
+    cpu = cpu_sample(host, dims, args.cpu_seconds, args.reduced)
+
+  line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None,
+      "dtype": "f16-storage/f32-math" if args.reduced else "f32", "data": "synthetic",
+      "config": {"workload": name, "grid": list(dims), "fdtd_steps": tt,
+                 "parallelism": "single GPU" if world == 1 else
+                 f"port batch: {world} independent engine runs, one per GPU, no collective",
+                 "l2": "working set (fields+coefficients) larger than L2; no flush needed",
+                 "plan": info},
+      "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+      "clocks": clocks,
+  }
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

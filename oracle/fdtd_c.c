@@ -62,7 +62,7 @@ int oracle_fdtd_num_outputs(const oracle_desc* d) {
 /* All pointers are host memory, C-order, z fastest:
  * eps (3,xx,yy,zz); source_field (2,1,Y,Z)|(2,X,1,Z)|(2,2,X,Y,1); waveform (tt,2);
  * mask (3,X,Y); kappa/sigma/alpha (Z,2); out (n_out,3,xx,yy,zz).
- * If steps_override > 0 only that many steps are run (CPU-baseline timing samples).
+ * If steps_override >= 0 only that many steps are run (0 = set-up only; CPU-baseline timing).
  * Returns 0 on success. */
 int oracle_fdtd_run(const oracle_desc* d, const float* eps, const float* source_field,
                     const float* waveform, const float* mask, const float* kappa,
@@ -114,7 +114,7 @@ int oracle_fdtd_run(const oracle_desc* d, const float* eps, const float* source_
     }
   float *Ex = E, *Ey = E + N, *Ez = E + 2 * N, *Hx = H, *Hy = H + N, *Hz = H + 2 * N;
   float *pHx = psiH, *pHy = psiH + N, *pEx = psiE, *pEy = psiE + N;
-  const int tt = steps_override > 0 && steps_override < d->tt ? steps_override : d->tt;
+  const int tt = steps_override >= 0 && steps_override < d->tt ? steps_override : d->tt;
   const int nout = oracle_fdtd_num_outputs(d);
   int oi = 0;
   for (int n = 0; n < tt; ++n) {

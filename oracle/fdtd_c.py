@@ -60,7 +60,7 @@ def max_threads():
 def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
           pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
           use_reduced_precision=False, launch_params=None, offset=(0, 0, 0),
-          nthreads=0, steps_override=0, want_output=True):
+          nthreads=0, steps_override=-1, want_output=True):
   eps, sf, wf = _f32(epsilon), _f32(source_field), _f32(source_waveform)
   mask, kap, sig, alp = (_f32(a) for a in (absorption_mask, pml_kappa, pml_sigma, pml_alpha))
   X, Y, Z = domain_shape(mask, kap)

@@ -24,6 +24,8 @@
 // with ld.global.cg because L1 is not coherent across SMs within a launch.
 #pragma once
 
+#include <stdio.h>
+
 #include <string>
 
 #include "fdtd_common.cuh"
@@ -430,6 +432,15 @@ bool systolic_configure(const Geom& g, int tile_y_req, int stages_req, int threa
   return true;
 }
 
+// Turns a timed-out wait (a dependency that never arrived) into a loud, sticky CUDA error.
+__global__ void systolic_check_kernel(const unsigned* status) {
+  if (*status != 0) {
+    printf("b200fdtd: systolic kernel gave up waiting on a dependency (first CTA %u)\n",
+           *status - 1);
+    __trap();
+  }
+}
+
 template <typename T>
 int systolic_launch(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
                     cudaStream_t st) {
@@ -442,7 +453,10 @@ int systolic_launch(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, uns
   void* args[] = {&gg, &pp, &cc, &sync};
   e = cudaLaunchCooperativeKernel((const void*)systolic_kernel<T>, dim3(cfg.stages * cfg.ntiles),
                                   dim3(cfg.threads), args, cfg.smem_bytes, st);
-  return (int)e;
+  if (e != cudaSuccess) return (int)e;
+  systolic_check_kernel<<<1, 1, 0, st>>>(
+      sync + (size_t)cfg.stages * cfg.ntiles * kSysFlagStride);
+  return (int)cudaGetLastError();
 }
 
 }  // namespace b200

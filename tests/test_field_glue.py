@@ -1,0 +1,125 @@
+"""field()/scatter() glue driven over the ORACLE engine on the CPU: input construction
+(mirrors /root/reference/src/pjz/_field.py:194-269), the straight-waveguide physics
+known-answer of SURVEY.md 8(c), reciprocity, and the scatter backward formula (:380-398)."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fdtd_c
+from pjz_b200 import SimParams, field, mode, scatter
+from pjz_b200 import _field as glue
+
+OMEGA = np.array([2 * np.pi / 37])
+
+
+def _waveguide(xx=60, yy=30, zz=20):
+  eps = np.ones((3, xx, yy, zz), np.float32)
+  eps[:, :, 9:21, 8:12] = 12.25       # the core of /root/reference/tests/test_modes.py:39-40
+  return eps
+
+
+def _params(tt=3600, **kw):
+  base = dict(omega_range=(OMEGA[0], OMEGA[0]), tt=tt, dt=0.5, absorption_padding=25,
+              absorption_coeff=4e-4, pml_widths=(10, 10), use_reduced_precision=False,
+              domain_zz=52)
+  base.update(kw)
+  return SimParams(**base)
+
+
+def test_engine_inputs_follow_reference_rules():
+  eps = _waveguide(20, 30, 20)
+  src = np.random.default_rng(0).standard_normal((2, 1, 30, 20)).astype(np.float32)
+  p = _params(tt=400, absorption_padding=5)
+  kw, omega, steps = glue.engine_inputs(eps, src, OMEGA, 7, p)
+  # x source at padded position 7+5=12 (even): channel 0 carries Im(rsin), channel 1 is zero
+  assert kw["source_position"] == 12
+  assert kw["source_field"].shape == (2, 1, 40, 52)
+  assert kw["absorption_mask"].shape == (3, 30, 40)
+  assert kw["pml_kappa"].shape == (52, 2) and np.all(kw["pml_kappa"] == 1)
+  assert kw["offset"] == (5, 5, 16)
+  interval = glue._sampling_interval(OMEGA[0], OMEGA[0], 1, 0.5)
+  assert steps == (400 - 2 * interval - 1, 400, interval) and len(range(*steps)) == 3
+  rs = glue._ramped_sin(OMEGA, 4.0, 4.0, 0.5, 400)
+  np.testing.assert_allclose(kw["source_waveform"][:, 0], rs.imag, atol=1e-6)
+  assert not kw["source_waveform"][:, 1].any()
+  # source = mode / epsilon on the transverse components (Ey, Ez) at the source plane
+  np.testing.assert_allclose(kw["source_field"][0, 0, 5:35, 16:36].numpy(),
+                             src[0, 0] / eps[1, 7], rtol=1e-6)
+  np.testing.assert_allclose(kw["source_field"][1, 0, 5:35, 16:36].numpy(),
+                             src[1, 0] / eps[2, 7], rtol=1e-6)
+  assert not kw["source_field"][:, :, :5].any()
+  # odd padded position -> +1 and swapped channels (:230-233)
+  kw2, _, _ = glue.engine_inputs(eps, src, OMEGA, 8, p)
+  assert kw2["source_position"] == 14
+  np.testing.assert_allclose(kw2["source_waveform"][:, 1], rs.imag, atol=1e-6)
+  assert not kw2["source_waveform"][:, 0].any()
+
+
+def test_engine_inputs_z_source_and_z_batch():
+  eps = _waveguide(12, 14, 20)
+  src = np.random.default_rng(1).standard_normal((2, 12, 14, 1)).astype(np.float32)
+  p = _params(tt=400, absorption_padding=3, use_z_as_batch=True)
+  kw, _, _ = glue.engine_inputs(eps, src, OMEGA, 4, p)
+  assert kw["source_field"].shape == (2, 2, 18, 20, 1)
+  assert kw["source_position"] == 4 + 16
+  assert not kw["source_field"][0].any()            # Im(real mode) = 0
+  assert np.all(np.isinf(kw["pml_kappa"])) and not kw["pml_sigma"].any()
+  rs = glue._ramped_sin(OMEGA, 4.0, 4.0, 0.5, 400)
+  np.testing.assert_allclose(kw["source_waveform"], np.stack([rs.imag, rs.real], -1), atol=1e-6)
+
+
+def test_reference_default_heights():
+  # pjz's own rule (no domain_zz): fp16 mode -> 128 - 32 = 96 planes, epsilon centred
+  eps = np.ones((3, 4, 4, 64), np.float32)
+  src = np.ones((2, 1, 4, 64), np.float32)
+  p = SimParams(omega_range=(OMEGA[0], OMEGA[0]), tt=200, absorption_padding=2)
+  kw, _, _ = glue.engine_inputs(eps, src, OMEGA, 1, p)
+  assert kw["pml_sigma"].shape == (96, 2) and kw["offset"] == (2, 2, 16)
+  assert kw["use_reduced_precision"] is True and kw["pml_widths"] == (16, 16)
+
+
+@pytest.fixture(scope="module")
+def waveguide_run():
+  eps = _waveguide()
+  beta, exc, _, _ = mode(eps[:, 10:11], OMEGA, 1)
+  m = exc[..., 0].copy()
+  m[:, 1] *= -1   # frame-consistent x-excitation (SURVEY.md 8c "known open issue in pjz")
+  sv = scatter(eps, OMEGA, [m, m], [beta[:, 0], beta[:, 0]], (10, 45), (True, False),
+               _params(), engine=fdtd_c.fdtdz)
+  return eps, beta, m, sv
+
+
+def test_straight_waveguide_s21(waveguide_run):
+  """SURVEY.md 8(c) physics KAT: |S21| in [0.99, 1.01], phase within 0.05 rad of -beta L,
+  tiny reflection."""
+  _, beta, _, sv = waveguide_run
+  s21 = complex(sv[0][1][0])
+  s11 = complex(sv[0][0][0])
+  assert 0.99 <= abs(s21) <= 1.01
+  expected = (-float(beta[0, 0]) * 35 + np.pi) % (2 * np.pi) - np.pi
+  assert abs(np.angle(s21) - expected) < 0.05
+  assert abs(s11) < 0.03
+
+
+def test_reciprocity(waveguide_run):
+  _, _, _, sv = waveguide_run
+  s21, s12 = complex(sv[0][1][0]), complex(sv[1][0][0])
+  assert abs(s21 - s12) < 0.02
+
+
+def test_scatter_backward_is_pjz_reciprocity_formula():
+  """d Re(S_01) / d epsilon == Re(E_0 E_1 / a_0) summed over omega (:380-398)."""
+  eps = _waveguide(24, 30, 20)
+  beta, exc, _, _ = mode(eps[:, 4:5], OMEGA, 1)
+  m = exc[..., 0]
+  p = _params(tt=300, absorption_padding=4)
+  args = (OMEGA, [m, m], [beta[:, 0], beta[:, 0]], (4, 18), (True, False), p)
+  e = torch.from_numpy(eps).requires_grad_(True)
+  sv = scatter(e, *args, engine=fdtd_c.fdtdz)
+  loss = torch.real(sv[0][1]).sum()
+  loss.backward()
+  _, grads, fields = glue._scatter_impl(torch.from_numpy(eps), *args, engine=fdtd_c.fdtdz)
+  want = torch.sum(torch.real(grads[0][1]), dim=0)
+  torch.testing.assert_close(e.grad, want, rtol=1e-5, atol=1e-7)
+  assert e.grad.shape == eps.shape and float(e.grad.abs().max()) > 0

@@ -1,0 +1,58 @@
+"""Port-batch sharding of scatter() across ranks (first axis): world_size-2
+gloo run on the CPU with the oracle engine must reproduce the single-process S-matrix."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _problem():
+  from pjz_b200 import SimParams, mode
+  omega = np.array([2 * np.pi / 37])
+  eps = np.ones((3, 20, 30, 20), np.float32)
+  eps[:, :, 9:21, 8:12] = 12.25
+  beta, exc, _, _ = mode(eps[:, 3:4], omega, 2)
+  modes = [exc[..., 0], exc[..., 1], exc[..., 0]]
+  betas = [beta[:, 0], beta[:, 1], beta[:, 0]]
+  p = SimParams(omega_range=(omega[0], omega[0]), tt=200, dt=0.5, absorption_padding=3,
+                absorption_coeff=4e-4, pml_widths=(4, 4), use_reduced_precision=False,
+                domain_zz=28)
+  return eps, omega, modes, betas, (3, 4, 16), (True, True, False), p
+
+
+def _worker(rank, world, port, out):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from oracle import fdtd_c
+  from pjz_b200 import scatter
+  eps, omega, modes, betas, pos, fwd, p = _problem()
+  sv = scatter(eps, omega, modes, betas, pos, fwd, p, engine=fdtd_c.fdtdz)
+  if rank == 0:
+    torch.save([[s.clone() for s in row] for row in sv], out)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_two_rank_scatter_matches_single_process(tmp_path):
+  from oracle import fdtd_c
+  from pjz_b200 import scatter
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "sv.pt")
+  mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+  got = torch.load(out)
+  eps, omega, modes, betas, pos, fwd, p = _problem()
+  want = scatter(eps, omega, modes, betas, pos, fwd, p, engine=fdtd_c.fdtdz)
+  for i in range(3):
+    for j in range(3):
+      torch.testing.assert_close(got[i][j], want[i][j], rtol=0, atol=0)
