@@ -71,7 +71,7 @@ def test_ramped_sin():
 
 
 def test_output_phases_and_projection_recover_phasor():
-  """Snapshots of Re(a e^{-i w t}) (the sign convention of the sin/cos rows,
+  """Snapshots of Re(a e^{+i w t}) (the sign convention of the cos / -sin rows,
   /root/reference/src/pjz/_field.py:142-150, 276-279) project back onto a."""
   import torch
   omega = np.array([2 * np.pi / 40, 2 * np.pi / 37])

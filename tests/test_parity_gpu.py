@@ -230,4 +230,5 @@ def test_field_through_cuda_engine_matches_oracle_engine():
   want = field(eps, exc[0, ..., 0], omega, 6, p, engine=fdtd_c.fdtdz)
   got = field(torch.from_numpy(eps).cuda(), exc[0, ..., 0], omega, 6, p)
   assert got.is_cuda and got.dtype == torch.complex64
-  torch.testing.assert_close(got.cpu(), want, rtol=0, atol=0)
+  # snapshots are bit-identical; the pinv projection einsum runs on the GPU vs the CPU
+  torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
