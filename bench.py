@@ -43,10 +43,11 @@ def parse():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="bend", choices=["bend", "waveguide", "demux", "coupler"])
   ap.add_argument("--tt", type=int, default=0, help="override the number of FDTD steps")
-  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic"])
+  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic", "systolic_async"])
   ap.add_argument("--tile-y", type=int, default=0)
   ap.add_argument("--stages", type=int, default=0)
   ap.add_argument("--threads", type=int, default=0)
+  ap.add_argument("--prefetch", type=int, default=0)
   ap.add_argument("--reduced", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
@@ -74,7 +75,8 @@ def make_workload(args, rank):
     params = params._replace(tt=args.tt)
     name += f" (tt overridden to {args.tt})"
   lp = {"kernel": args.kernel}
-  for k, v in (("tile_y", args.tile_y), ("stages", args.stages), ("threads", args.threads)):
+  for k, v in (("tile_y", args.tile_y), ("stages", args.stages), ("threads", args.threads),
+               ("prefetch", args.prefetch)):
     if v:
       lp[k] = v
   params = params._replace(launch_params=lp)
@@ -301,8 +303,9 @@ def main():
   per_gpu = value / world
   achieved = per_gpu * bpc                       # GB/s of ALGORITHMIC traffic
   traffic = ncu_traffic()
-  if info["kernel"] == "systolic":
-    dominant = "systolic_kernel (1 launch per engine call; duration = call time incl. 3 prep kernels)"
+  if info["kernel"].startswith("systolic"):
+    dominant = (("systolic2_kernel" if info["kernel"] == "systolic_async" else "systolic_kernel") +
+                " (1 launch per engine call; duration = call time incl. 3 prep kernels)")
     launches = (3 + 2) * args.steps
   else:
     dominant = "twopass_h_kernel + twopass_e_kernel (2 launches per FDTD step)"
@@ -310,7 +313,7 @@ def main():
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
               "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
               "kernel": dominant, "peak_source": peak_src,
-              "algorithmic_bytes_per_launch": bpc * cells * (tt if info["kernel"] == "systolic" else 0.5),
+              "algorithmic_bytes_per_launch": bpc * cells * (tt if info["kernel"].startswith("systolic") else 0.5),
               "bytes_per_cell_update": bpc}
 
   cpu = None

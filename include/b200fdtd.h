@@ -70,7 +70,10 @@ enum {
 enum {
   B200FDTD_KERNEL_AUTO = 0,
   B200FDTD_KERNEL_TWOPASS = 1,  /* one H launch + one E launch per step, in place          */
-  B200FDTD_KERNEL_SYSTOLIC = 2  /* one persistent launch: fused H+E, x-sweep, L2-pipelined  */
+  B200FDTD_KERNEL_SYSTOLIC = 2, /* one persistent launch: fused H+E x-sweep, L2-pipelined
+                                   stages, operands staged through registers               */
+  B200FDTD_KERNEL_SYSTOLIC_ASYNC = 3 /* same protocol; operands staged through a cp.async
+                                   shared-memory ring, dedicated sync warp (the fast path)  */
 };
 
 /* Static description of one engine call (everything that is a python scalar/tuple at
@@ -93,7 +96,8 @@ typedef struct b200fdtd_desc {
   int32_t tile_y;               /* systolic: y-columns owned per CTA                        */
   int32_t stages;               /* systolic: time steps in flight along the x sweep         */
   int32_t threads;              /* CTA size override                                        */
-  int32_t reserved[4];
+  int32_t prefetch;             /* systolic_async: planes of prefetch distance (1..3)       */
+  int32_t reserved[3];
 } b200fdtd_desc;
 
 /* ABI version of the loaded library. */

@@ -17,6 +17,7 @@
 
 #include "fdtd_common.cuh"
 #include "kernels_systolic.cuh"
+#include "kernels_systolic2.cuh"
 #include "kernels_twopass.cuh"
 
 namespace b200 {
@@ -68,7 +69,7 @@ static int validate(const b200fdtd_desc* d) {
     return fail(B200FDTD_EINVAL, "output_steps (%d,%d,%d) outside [0,tt=%d)", d->out_start,
                 d->out_stop, d->out_step, d->tt);
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
-  if (d->kernel < 0 || d->kernel > 2) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  if (d->kernel < 0 || d->kernel > 3) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
   return B200FDTD_OK;
 }
 
@@ -102,8 +103,13 @@ static Geom make_geom(const b200fdtd_desc* d) {
 
 struct Plan {
   int kernel;            // resolved B200FDTD_KERNEL_*
-  SystolicCfg sys;       // valid when kernel == SYSTOLIC
+  int depth;             // prefetch distance (SYSTOLIC_ASYNC)
+  SystolicCfg sys;       // valid for the systolic kernels
 };
+
+static bool is_systolic(int k) {
+  return k == B200FDTD_KERNEL_SYSTOLIC || k == B200FDTD_KERNEL_SYSTOLIC_ASYNC;
+}
 
 static int device_props(int* sms, int* l2_bytes) {
   int dev = 0;
@@ -114,19 +120,49 @@ static int device_props(int* sms, int* l2_bytes) {
 }
 
 template <typename T>
-static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
-  plan->kernel = d->kernel == B200FDTD_KERNEL_AUTO ? B200FDTD_KERNEL_SYSTOLIC : d->kernel;
-  if (plan->kernel == B200FDTD_KERNEL_SYSTOLIC) {
-    int sms = 0, l2 = 0;
-    int rc = device_props(&sms, &l2);
-    if (rc) return rc;
-    std::string why;
-    if (!systolic_configure<T>(g, d->tile_y, d->stages, d->threads, sms, l2, &plan->sys, &why)) {
-      if (d->kernel == B200FDTD_KERNEL_SYSTOLIC)
-        return fail(B200FDTD_EUNSUPPORTED, "systolic kernel unavailable: %s", why.c_str());
-      plan->kernel = B200FDTD_KERNEL_TWOPASS;
-    }
+static bool configure_async(const Geom& g, const b200fdtd_desc* d, int depth, int sms, int l2,
+                            SystolicCfg* cfg, std::string* why) {
+  switch (depth) {
+    case 1: return systolic2_configure_d<T, 1>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
+    case 2: return systolic2_configure_d<T, 2>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
+    case 3: return systolic2_configure_d<T, 3>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
   }
+  *why = "prefetch must be 1, 2 or 3";
+  return false;
+}
+
+// AUTO: cp.async-staged systolic kernel with the deepest ring that fits (2 preferred), else the
+// register-staged one, else the per-step kernels.
+template <typename T>
+static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
+  plan->kernel = d->kernel;
+  plan->depth = 0;
+  if (d->kernel == B200FDTD_KERNEL_TWOPASS) return B200FDTD_OK;
+  int sms = 0, l2 = 0;
+  int rc = device_props(&sms, &l2);
+  if (rc) return rc;
+  std::string why;
+  if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {
+    const int order[3] = {2, 1, 3};
+    for (int i = 0; i < 3; ++i) {
+      const int depth = d->prefetch > 0 ? d->prefetch : order[i];
+      if (configure_async<T>(g, d, depth, sms, l2, &plan->sys, &why)) {
+        plan->kernel = B200FDTD_KERNEL_SYSTOLIC_ASYNC;
+        plan->depth = depth;
+        return B200FDTD_OK;
+      }
+      if (d->prefetch > 0 || i == 1) break;
+    }
+    if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC)
+      return fail(B200FDTD_EUNSUPPORTED, "systolic_async kernel unavailable: %s", why.c_str());
+  }
+  if (systolic_configure<T>(g, d->tile_y, d->stages, d->threads, sms, l2, &plan->sys, &why)) {
+    plan->kernel = B200FDTD_KERNEL_SYSTOLIC;
+    return B200FDTD_OK;
+  }
+  if (d->kernel == B200FDTD_KERNEL_SYSTOLIC)
+    return fail(B200FDTD_EUNSUPPORTED, "systolic kernel unavailable: %s", why.c_str());
+  plan->kernel = B200FDTD_KERNEL_TWOPASS;
   return B200FDTD_OK;
 }
 
@@ -271,8 +307,13 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
   CUDA_TRY(cudaGetLastError());
 
   if (g.tt == 0) return B200FDTD_OK;
-  if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) {
-    int rc = systolic_launch<T>(g, p, plan.sys, reinterpret_cast<unsigned*>(ws + w.sync), st);
+  if (is_systolic(plan.kernel)) {
+    unsigned* sync = reinterpret_cast<unsigned*>(ws + w.sync);
+    int rc;
+    if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
+    else if (plan.depth == 1) rc = systolic2_launch_d<T, 1>(g, p, plan.sys, sync, st);
+    else if (plan.depth == 2) rc = systolic2_launch_d<T, 2>(g, p, plan.sys, sync, st);
+    else rc = systolic2_launch_d<T, 3>(g, p, plan.sys, sync, st);
     if (rc != 0)
       return fail(B200FDTD_ECUDA, "systolic launch failed: %s",
                   cudaGetErrorString((cudaError_t)rc));
@@ -306,7 +347,7 @@ static int run_impl(const b200fdtd_desc* d, const void* const* in, void* const* 
   if (plan.kernel == B200FDTD_KERNEL_TWOPASS && g.X > 65535)
     return fail(B200FDTD_EUNSUPPORTED, "two-pass kernel supports X <= 65535");
   const Workspace w = carve(g, d->use_reduced_precision != 0,
-                            plan.kernel == B200FDTD_KERNEL_SYSTOLIC, &plan.sys);
+                            is_systolic(plan.kernel), &plan.sys);
   char* ws = static_cast<char*>(ws_in);
   bool own = false;
   if (!ws) {
@@ -353,8 +394,7 @@ size_t b200fdtd_workspace_bytes(const b200fdtd_desc* desc) {
   const Geom g = make_geom(desc);
   Plan plan;
   if (make_plan(desc, g, &plan)) return 0;
-  return carve(g, desc->use_reduced_precision != 0, plan.kernel == B200FDTD_KERNEL_SYSTOLIC,
-               &plan.sys).total;
+  return carve(g, desc->use_reduced_precision != 0, is_systolic(plan.kernel), &plan.sys).total;
 }
 
 int b200fdtd_run(const b200fdtd_desc* desc, const void* const* inputs, void* const* outputs,
@@ -447,14 +487,13 @@ int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
   if (rc) return rc;
   memset(info, 0, 8 * sizeof(int64_t));
   info[0] = plan.kernel;
-  if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) {
+  if (is_systolic(plan.kernel)) {
     info[1] = plan.sys.tile_y; info[2] = plan.sys.stages; info[3] = plan.sys.threads;
     info[4] = (int64_t)plan.sys.stages * plan.sys.ntiles; info[5] = plan.sys.smem_bytes;
-    info[6] = 1; info[7] = plan.sys.l2_window_bytes >> 20;
+    info[6] = plan.depth; info[7] = plan.sys.l2_window_bytes >> 20;
   } else {
     info[3] = kTwoPassThreads;
     info[4] = (int64_t)((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads) * g.X;
-    info[6] = 2LL * g.tt;
   }
   return B200FDTD_OK;
 }

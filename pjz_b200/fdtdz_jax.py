@@ -10,7 +10,8 @@ current stream and the result is a CUDA tensor) or anything ``np.asarray`` accep
 ``b200fdtd_run_host`` copies up, runs, copies the snapshots back; the result is a NumPy array).
 
 ``launch_params`` (opaque in pjz, ``SimParams.launch_params`` :53) may be ``None`` or a dict with
-any of ``kernel`` ("auto" | "twopass" | "systolic"), ``tile_y``, ``stages``, ``threads``.
+any of ``kernel`` ("auto" | "twopass" | "systolic" | "systolic_async"), ``tile_y``, ``stages``,
+``threads``, ``prefetch``.
 To make ``import fdtdz_jax`` resolve to this module: ``pjz_b200.fdtdz_jax.install()``.
 """
 
@@ -26,7 +27,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fdtd.so")
 
 NUM_INPUTS = 7
-_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2}
+_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2, "systolic_async": 3}
 ABI_VERSION = 1
 
 
@@ -38,8 +39,9 @@ class Desc(ctypes.Structure):
                   "source_axis", "source_position", "pml_lo", "pml_hi", "out_start",
                   "out_stop", "out_step", "use_reduced_precision")] +
               [("dt", ctypes.c_float)] +
-              [(n, ctypes.c_int32) for n in ("kernel", "tile_y", "stages", "threads")] +
-              [("reserved", ctypes.c_int32 * 4)])
+              [(n, ctypes.c_int32) for n in ("kernel", "tile_y", "stages", "threads",
+                                             "prefetch")] +
+              [("reserved", ctypes.c_int32 * 3)])
 
 
 _lib = None
@@ -126,15 +128,17 @@ def make_desc(epsilon, dt, source_field, source_waveform, source_position, absor
   d.dt = float(dt)
   lp = launch_params or {}
   if not isinstance(lp, dict):
-    raise ValueError("launch_params must be None or a dict (kernel, tile_y, stages, threads)")
-  unknown = set(lp) - {"kernel", "tile_y", "stages", "threads"}
+    raise ValueError("launch_params must be None or a dict (kernel, tile_y, stages, threads, "
+                     "prefetch)")
+  unknown = set(lp) - {"kernel", "tile_y", "stages", "threads", "prefetch"}
   if unknown:
     raise ValueError(f"unknown launch_params keys {sorted(unknown)}")
   k = lp.get("kernel", "auto")
   if k not in _KERNELS:
     raise ValueError(f"launch_params['kernel'] must be one of {sorted(_KERNELS)}, got {k!r}")
   d.kernel = _KERNELS[k]
-  d.tile_y, d.stages, d.threads = (int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads"))
+  d.tile_y, d.stages, d.threads, d.prefetch = (
+      int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads", "prefetch"))
   rc = lib().b200fdtd_validate(ctypes.byref(d))
   if rc != 0:
     raise ValueError(_last_error())
@@ -209,7 +213,7 @@ def plan_info(**kwargs):
   rc = lib().b200fdtd_plan_info(ctypes.byref(d), info)
   if rc != 0:
     raise RuntimeError(_last_error())
-  names = ("kernel", "tile_y", "stages", "threads", "ctas", "smem_bytes", "launches_per_run",
+  names = ("kernel", "tile_y", "stages", "threads", "ctas", "smem_bytes", "prefetch",
            "l2_window_mib")
   out = dict(zip(names, (int(v) for v in info)))
   out["kernel"] = {v: k for k, v in _KERNELS.items()}[out["kernel"]]

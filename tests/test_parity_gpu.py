@@ -25,7 +25,7 @@ from tests.problems import random_problem, rel_l2
 pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "engine_golden.npz"))
-KERNELS = ["twopass", "systolic"]
+KERNELS = ["twopass", "systolic", "systolic_async"]
 FP32_TOL = 1e-5
 
 
@@ -83,6 +83,16 @@ def test_ragged_and_degenerate_domains(domain, pml, kernel):
     np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
 
 
+@pytest.mark.parametrize("prefetch", [1, 2, 3])
+@pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (6, 3), (4, 40)])
+def test_systolic_async_tilings(tile_y, stages, prefetch):
+  kw = random_problem(domain=(11, 23, 16), axis=1, pml=(4, 4), tt=45, seed=13,
+                      output_steps=(20, 45, 6))
+  want = fdtd_c.fdtdz(**kw)
+  out = run_gpu(kw, kernel="systolic_async", tile_y=tile_y, stages=stages, prefetch=prefetch)
+  np.testing.assert_array_equal(out, want)
+
+
 @pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (5, 3), (14, 7), (4, 40)])
 def test_systolic_tilings(tile_y, stages):
   """Every tiling / pipeline depth must give the same bits (many stages on a short x extent
@@ -124,7 +134,7 @@ def test_host_path_equals_device_path():
 def test_auto_plan_prefers_systolic_and_reports():
   kw = random_problem(domain=(64, 64, 64), tt=20, seed=1)
   info = fdtdz_jax.plan_info(**kw)
-  assert info["kernel"] == "systolic" and info["ctas"] >= 1 and info["launches_per_run"] == 1
+  assert info["kernel"] == "systolic_async" and info["ctas"] >= 1 and info["prefetch"] >= 1
 
 
 def test_no_outputs_and_zero_steps():
@@ -143,6 +153,7 @@ def test_schedule_selection_and_linearity_large():
   a = run_gpu(kw, kernel="twopass")
   b = run_gpu(kw, kernel="systolic")
   np.testing.assert_array_equal(a, b)
+  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_async"))
   assert np.isfinite(a).all() and np.abs(a).max() > 0
   kw2 = dict(kw); kw2["output_steps"] = (5, 16, 10)
   np.testing.assert_array_equal(run_gpu(kw2), a[1:4:2])
