@@ -44,6 +44,7 @@ struct SystolicCfg {
   int max_lead;          // a stage may run at most this many planes ahead of the next stage
   int need_zfix;         // z-columns straddle warps (Zq does not divide 32)
   int trap_on_timeout;
+  int pf_ahead;          // systolic_async: planes of L2 prefetch beyond the staging ring
   long long l2_window_bytes;
 };
 

@@ -1,22 +1,35 @@
-// Systolic kernel, second generation: same decomposition and dependency protocol as
-// kernels_systolic.cuh (read its header first), re-plumbed so that neither memory latency nor
-// inter-CTA synchronisation sits on the compute warps' critical path.
+// Systolic kernel, asynchronous generation ("systolic_async"): same decomposition and
+// dependency protocol as kernels_systolic.cuh (read its header first), re-plumbed so that
+// neither memory latency nor inter-CTA synchronisation sits on the compute warps' critical path.
 //
 //  * Operand staging.  Every compute thread copies the 16-byte vectors of ITS OWN cells
-//    (E^n[P+1], H^{n-1/2}[P], psi[P]) from global/L2 into a shared-memory ring with
-//    cp.async.cg (LDGSTS, L1-bypassing, no registers held) D iterations before they are used.
-//    x+1, y+1 and cross-warp z+1 neighbours are then plain shared-memory reads of the
-//    neighbouring threads' slots: there is no exchange copy for E at all.
-//      ring depth:  E needs D+2 plane slots (P and P+1 are both live), H and psi D+1.
-//  * A dedicated sync warp (the last warp of the CTA) polls the predecessor stage's progress
-//    counters D iterations ahead and publishes this CTA's own progress with st.release.gpu
-//    after the barrier that follows the stores, so compute warps never execute an acquire
-//    load, a fence or a spin.
-//  * Two CTA barriers per plane: (A) "ring slot landed + previous stores issued",
-//    (B) compute-warps-only exchange of the freshly formed H for the y-1 / z-1 neighbours.
+//    (E^n[P+1], H^{n-1/2}[P], B[P], psi[P]) from L2 into a shared-memory ring with cp.async.cg
+//    (LDGSTS, L1-bypassing, no registers held) D iterations before they are used.  x+1, y+1
+//    and cross-warp z+1 neighbours are then plain shared-memory reads of the neighbouring
+//    threads' slots: there is no exchange copy for E at all.
+//      ring depth:  E needs D+2 plane slots (P and P+1 are both live); H, B and psi D+1.
+//  * L2 prefetch.  The ring only hides L2 latency.  The stage that currently leads the window
+//    reads planes nobody touched for a whole sweep, i.e. from HBM; the poller warp therefore
+//    issues cp.async.bulk.prefetch.L2 for the tile's (contiguous) column range several planes
+//    ahead of the ring, so every ring load is an L2 hit.
+//  * Decoupled synchronisation.  Two service warps replace the spin/fence of the register
+//    kernel:
+//      - the POLLER continuously ld.acquire.gpu's the three predecessor counters (+ the
+//        successor's, for the max_lead throttle) and mirrors them into shared memory;
+//      - the PUBLISHER watches a shared-memory "iterations finished" word and, whenever it
+//        advances, performs the st.release.gpu (fence included) of this CTA's counter.
+//    Compute warps only read/write those shared-memory words (acquire/release at CTA scope),
+//    so an L2 round trip or a fence never stalls them; if a service warp is slower than an
+//    iteration it simply coalesces updates.
+//  * Two compute-only CTA barriers per plane: (A) "ring slot landed, previous iteration's
+//    shared-memory reads done", (B) exchange of the freshly formed H for the y-1/z-1 neighbours.
+//
+// Register budget: registers are partitioned per SM sub-partition, so at most 16 warps can hold
+// more than 96 registers each; the CTA is therefore capped at 14 compute + 2 service warps.
 #pragma once
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -25,7 +38,8 @@
 
 namespace b200 {
 
-constexpr int kSys2MaxCompute = 512;
+constexpr int kSys2MaxCompute = 448;   // 14 warps
+constexpr int kSys2Service = 64;       // poller warp + publisher warp
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -41,19 +55,51 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void bar_compute(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
+// Barrier over the compute warps that also AND-reduces a predicate (uniform failure decisions).
+__device__ __forceinline__ bool bar_compute_and(int nthreads, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "bar.red.and.pred p, 1, %1, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "r"(nthreads), "r"((int)pred) : "memory");
+  return r != 0;
+}
+__device__ __forceinline__ unsigned ld_acquire_cta(const unsigned* smem_word) {
+  unsigned v;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_word);
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta(unsigned* smem_word, unsigned v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_word);
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// Shared control block of one CTA.
+struct Sys2Ctl {
+  unsigned avail;     // min over the three predecessor counters (raw, cumulative)
+  unsigned next;      // successor stage's counter on this tile
+  unsigned done;      // this CTA's cumulative count of finished sweep indices
+  unsigned front;     // cumulative iteration index the compute warps have reached (for prefetch)
+  unsigned ok;        // 0 once any CTA gave up
+  unsigned exit_;     // compute warps are finished
+};
 
 template <typename T, int D>
-// 17 warps x 120 registers = 65 280 <= 64 Ki: __launch_bounds__(544) would round the CTA up to 20
-// warps and cap the kernel at 96 registers (spills).
-__global__ void __maxnreg__(120)
+__global__ void __launch_bounds__(kSys2MaxCompute + kSys2Service)
 systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sync) {
   constexpr int VW = VecTraits<T>::VW;
   constexpr int NE = D + 2, NH = D + 1;
   constexpr int PV = VW / 4;                     // float4 per psi vector
   extern __shared__ float4 smem[];
-  const int NTc = blockDim.x - 32;               // compute threads
+  __shared__ Sys2Ctl ctl;
+  const int NTc = blockDim.x - kSys2Service;     // compute threads
   const int tid = threadIdx.x, lane = tid & 31;
-  const bool is_sync_warp = tid >= NTc;
   const int S = cfg.stages, NT = cfg.ntiles;
   const int t = blockIdx.x % NT, j = blockIdx.x / NT;
   const int y0 = (int)((long long)t * g.Y / NT);
@@ -62,46 +108,83 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 
   float4* const sE = smem;                                   // [NE][3][NTc]
   float4* const sH = sE + (size_t)NE * 3 * NTc;              // [NH][3][NTc]
-  float4* const sX = sH + (size_t)NH * 3 * NTc;              // [3][NTc]  Hz, Hx, Hy (new)
+  float4* const sB = sH + (size_t)NH * 3 * NTc;              // [NH][3][NTc]
+  float4* const sX = sB + (size_t)NH * 3 * NTc;              // [3][NTc]  Hz, Hx, Hy (new)
   float4* const sP = sX + (size_t)3 * NTc;                   // [NH][4][npsi]
-  __shared__ int s_ok;
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
 
-  // =================================== sync warp =================================================
-  if (is_sync_warp) {
+  if (tid == 0) {
+    ctl.avail = 0; ctl.next = 0; ctl.done = 0; ctl.front = 0; ctl.ok = 1; ctl.exit_ = 0;
+  }
+  __syncthreads();
+
+  // =================================== poller warp ===============================================
+  if (tid >= NTc && tid < NTc + 32) {
     const int jp = (j + S - 1) % S, jn = (j + 1) % S;
-    const unsigned* watch = nullptr;
-    if (lane < 3) watch = sync + ((size_t)jp * NT + wrapi(t - 1 + lane, NT)) * kSysFlagStride;
-    else if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
-    bool ok = true;
-    for (int n = j; n < g.tt && ok; n += S) {
-      const int m = n / S;
-      const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)g.X;
-      const unsigned base_mine = (unsigned)m * (unsigned)g.X;
-      const bool has_prev = n > 0, has_next = n + 1 < g.tt;
-      // Iteration i (0 = prologue) works on sweep index k = i-1.  Before barrier A_i the loads of
-      // iteration i+D are about to be issued: they touch planes up to index (i+D-1)+2 of the
-      // previous stage's sweep.  The pre-loop (i = -1) covers the groups of iterations 0..D-1.
-      for (int i = -1; i <= g.X && ok; ++i) {
-        const int ahead = i + D;                   // last iteration whose loads get issued
-        if (lane < 3 && has_prev) {
-          const int need = min(max(ahead, 0) + 2, g.X);
-          ok = wait_ge(watch, base_prev + (unsigned)need, status);
-        } else if (lane == 3 && has_next && j + 1 < S) {
-          const int kk = min(ahead, g.X) - 1;      // index this CTA is about to prefetch
-          if (kk > cfg.max_lead)
-            ok = wait_ge(watch, base_mine + (unsigned)(kk - cfg.max_lead), status);
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        if (lane == 0) s_ok = ok;
-        __syncthreads();                           // A_i  (i = -1: the pre-loop barrier)
-        // all stores of iteration i-1 (index i-2) are issued: publish it.
-        if (lane == 0 && i >= 2) st_release_u32(my_prog, base_mine + (unsigned)(i - 1));
+    const unsigned* watch = sync + ((size_t)jp * NT + wrapi(t - 1 + (lane < 3 ? lane : 1), NT)) *
+                                       kSysFlagStride;
+    if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
+    if (lane == 4) watch = status;
+    // L2 prefetch duty: lanes 8..16 own one array each (E0,E1,E2,H0,H1,H2 of the read set, B0..2).
+    const int ylo = max(y0 - 1, 0), yhi = min(y0 + Yt, g.Y - 1);
+    const unsigned pf_bytes = (unsigned)((yhi - ylo + 1) * g.Zp * (int)sizeof(T));
+    const size_t pf_off = (size_t)ylo * g.Zp;
+    unsigned pf_done = 0;                          // cumulative iterations already prefetched
+    const unsigned sweep_iters = (unsigned)g.X + 1u;
+    while (ld_acquire_cta(&ctl.exit_) == 0) {
+      unsigned v = 0xffffffffu;
+      if (lane < 5) v = ld_acquire_u32(watch);
+      const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
+                     v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
+                     v4 = __shfl_sync(0xffffffffu, v, 4);
+      if (lane == 0) {
+        st_release_cta(&ctl.avail, min(v0, min(v1, v2)));
+        st_release_cta(&ctl.next, v3);
+        if (v4 != 0) st_release_cta(&ctl.ok, 0u);
       }
-      __syncthreads();                             // end of sweep: last iteration's stores issued
-      if (lane == 0 && ok) st_release_u32(my_prog, base_mine + (unsigned)g.X);
+      // prefetch the planes of iterations [front + D, front + D + pf_ahead) into L2
+      const unsigned front = ld_acquire_cta(&ctl.front);
+      const unsigned want = front + (unsigned)D + (unsigned)cfg.pf_ahead;
+      if (cfg.pf_ahead > 0 && lane >= 8 && lane < 17) {
+        if (pf_done < front + (unsigned)D) pf_done = front + (unsigned)D;
+        for (; pf_done < want; ++pf_done) {
+          const unsigned sweep = pf_done / sweep_iters, it = pf_done % sweep_iters;
+          const int n = j + (int)sweep * S;
+          if (n >= g.tt) break;
+          const int rb = n & 1;
+          const int P = wrapi(n % g.X - 1 + (int)it, g.X), Pn = wrapi(P + 1, g.X);
+          const int a = lane - 8;
+          const T* base;
+          int plane;
+          if (a < 3) { base = rb ? p.E2[a] : p.E[a]; plane = Pn; }
+          else if (a < 6) { base = rb ? p.H2[a - 3] : p.H[a - 3]; plane = P; }
+          else { base = p.B[a - 6]; plane = P; }
+          prefetch_l2_bulk(base + (size_t)plane * g.P + pf_off, pf_bytes);
+        }
+      }
+      pf_done = __shfl_sync(0xffffffffu, pf_done, 8);
+      __nanosleep(100);
+    }
+    return;
+  }
+  // ================================== publisher warp =============================================
+  if (tid >= NTc + 32) {
+    if (lane == 0) {
+      unsigned last = 0;
+      while (true) {
+        const unsigned ex = ld_acquire_cta(&ctl.exit_);
+        const unsigned d = ld_acquire_cta(&ctl.done);
+        if (d != last) {
+          st_release_u32(my_prog, d);              // fence.acq_rel.gpu + store
+          last = d;
+        } else if (ex) {
+          break;
+        } else {
+          __nanosleep(50);
+        }
+      }
     }
     return;
   }
@@ -122,9 +205,10 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
   const bool top = q + 1 == g.Zq, bottom = q == 0;
   const size_t XY = (size_t)g.X * g.Y;
+  bool ok = true;
 
   // CPML tables of this z-group are re-read from L1 (ld.global.nc, 3 KB total) where used:
-  // holding all six in registers costs 6*VW registers for the whole kernel.
+  // holding all six in registers would cost 6*VW registers for the whole kernel.
   auto load_tab = [&](int which, float (&dst)[VW]) {
 #pragma unroll
     for (int v = 0; v < VW; v += 4) {
@@ -133,7 +217,12 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     }
   };
 
-  for (int n = j; n < g.tt; n += S) {
+  unsigned iters_done = 0;                         // cumulative iterations finished (for front)
+  for (int n = j; n < g.tt && ok; n += S) {
+    const int m = n / S;
+    const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)g.X;
+    const unsigned base_mine = (unsigned)m * (unsigned)g.X;
+    const bool has_prev = n > 0, has_next = n + 1 < g.tt && j + 1 < S;
     const int rb = n & 1;
     const T* const Er0 = rb ? p.E2[0] : p.E[0];
     const T* const Er1 = rb ? p.E2[1] : p.E[1];
@@ -155,11 +244,38 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     const int oi = snapshot_index(g, n);
     const float w0 = __ldg(p.wave + 2 * (size_t)n), w1 = __ldg(p.wave + 2 * (size_t)n + 1);
 
-    // Issues the async copies that iteration `it` consumes: E[P_it + 1], H[P_it], psi[P_it]
-    // (+ E[P_0] for the very first one).  P_it = cstart - 1 + it.
+    // Blocks until the loads of iteration `it` are allowed: they read planes up to sweep index
+    // it+1 of the previous stage, which therefore must have finished it+2 indices on the tiles
+    // t-1, t, t+1 (the k+3 rule); and they must not run more than max_lead indices ahead of the
+    // next stage (keeps the planes in flight inside L2).  Spins on shared memory only.
+    auto wait_deps = [&](int it) {
+      const unsigned need = base_prev + (unsigned)min(it + 2, g.X);
+      const int lead = min(it, g.X) - 1 - cfg.max_lead;
+      const unsigned need_next = base_mine + (unsigned)max(lead, 0);
+      unsigned long long t0 = 0;
+      unsigned spins = 0;
+      while (true) {
+        const bool a = !has_prev || ld_acquire_cta(&ctl.avail) >= need;
+        const bool b = !has_next || lead <= 0 || ld_acquire_cta(&ctl.next) >= need_next;
+        if (a && b) return true;
+        if (ld_acquire_cta(&ctl.ok) == 0) return false;
+        if ((++spins & 255u) == 0) {
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 5000000000ull) {
+            atomicCAS(status, 0u, 1u + blockIdx.x);
+            st_release_cta(&ctl.ok, 0u);
+            return false;
+          }
+        }
+      }
+    };
+
+    // Issues the async copies that iteration `it` consumes: E[P_it + 1], H[P_it], B[P_it],
+    // psi[P_it] (+ E[P_0] for the very first one).  P_it = cstart - 1 + it.
     auto issue = [&](int it) {
       if (it <= g.X && active) {
-        const int P = wrapi(cstart - 1 + it - (it > g.X ? g.X : 0), g.X);
+        const int P = wrapi(cstart - 1 + it, g.X);
         const int Pn = wrapi(P + 1, g.X);
         const size_t offP = (size_t)P * g.P + coff, offN = (size_t)Pn * g.P + coff;
         float4* e = sE + (size_t)((it + 1) % NE) * 3 * NTc + tid;
@@ -177,6 +293,12 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
           cp_async16(h, Hr0 + offP);
           cp_async16(h + NTc, Hr1 + offP);
           cp_async16(h + 2 * NTc, Hr2 + offP);
+          if (own && it >= 1) {
+            float4* b = sB + (size_t)(it % NH) * 3 * NTc + tid;
+            cp_async16(b, p.B[0] + offP);
+            cp_async16(b + NTc, p.B[1] + offP);
+            cp_async16(b + 2 * NTc, p.B[2] + offP);
+          }
           if (has_psi) {
             float4* ps = sP + (size_t)(it % NH) * 4 * npsi + pidx;
             const size_t po = (size_t)P * pplane + poff;
@@ -195,37 +317,43 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       cp_async_commit();
     };
 
-    __syncthreads();                               // A_{-1}: dependencies of iterations 0..D-1
-    if (!s_ok) break;
+    // A failed wait (timeout / another CTA gave up) is turned into a CTA-uniform decision at the
+    // next AND-reducing barrier, so all compute threads leave the loops at the same point.
 #pragma unroll
-    for (int it = 0; it < D; ++it) issue(it);
+    for (int it = 0; it < D; ++it) {
+      ok = ok && wait_deps(it);
+      if (ok) issue(it); else cp_async_commit();
+    }
+    ok = bar_compute_and(NTc, ok);
 
     float hyp[VW], hzp[VW];
 #pragma unroll
-    for (int i = 0; i < VW; ++i) { hyp[i] = 0.f; hzp[i] = 0.f; }
+    for (int v = 0; v < VW; ++v) { hyp[v] = 0.f; hzp[v] = 0.f; }
+    float a0n = 0.f, a1n = 0.f, a2n = 0.f;       // absorber row of the NEXT plane (prefetched)
 
-    for (int i = 0; i <= g.X; ++i) {               // i = 0 is the prologue plane cstart-1
-      const int P = wrapi(cstart - 1 + i - (i > g.X ? g.X : 0), g.X);
+    for (int i = 0; i <= g.X && ok; ++i) {         // i = 0 is the prologue plane cstart-1
+      const int P = wrapi(cstart - 1 + i, g.X);
       const size_t offP = (size_t)P * g.P + coff;
       const bool real = i >= 1;
       cp_async_wait<D - 1>();
-      __syncthreads();                             // A_i
-      if (!s_ok) break;
-      issue(i + D);
+      bar_compute(NTc);                            // A_i
+      if (tid == 0) {
+        // every store of iterations < i has been issued by all compute threads
+        if (i >= 2) st_release_cta(&ctl.done, base_mine + (unsigned)(i - 1));
+        st_release_cta(&ctl.front, iters_done + (unsigned)i);
+      }
+      ok = wait_deps(i + D);
+      if (ok) issue(i + D); else cp_async_commit();
 
-      float4 bb0, bb1, bb2;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      bb0 = bb1 = bb2 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (own && real) {
-        bb0 = ld16<LD_NC>(p.B[0] + offP);
-        bb1 = ld16<LD_NC>(p.B[1] + offP);
-        bb2 = ld16<LD_NC>(p.B[2] + offP);
-        const size_t xy = (size_t)P * g.Y + y;
-        a0 = __ldg(p.A + xy); a1 = __ldg(p.A + XY + xy); a2 = __ldg(p.A + 2 * XY + xy);
+      const float a0 = a0n, a1 = a1n, a2 = a2n;
+      if (own && i < g.X) {
+        const size_t xy = (size_t)wrapi(P + 1, g.X) * g.Y + y;
+        a0n = __ldg(p.A + xy); a1n = __ldg(p.A + XY + xy); a2n = __ldg(p.A + 2 * XY + xy);
       }
       const float4* eC = sE + (size_t)(i % NE) * 3 * NTc;         // E^n[P]
       const float4* eN = sE + (size_t)((i + 1) % NE) * 3 * NTc;   // E^n[P+1]
       const float4* hO = sH + (size_t)(i % NH) * 3 * NTc;         // H^{n-1/2}[P]
+      const float4* bC = sB + (size_t)(i % NH) * 3 * NTc;         // B[P]
       const float4* pS = sP + (size_t)(i % NH) * 4 * npsi + pidx;
 
       float ex[VW], ey[VW], ez[VW], ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW];
@@ -265,12 +393,13 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         hx[v] = round_store<T>(hx[v]); hy[v] = round_store<T>(hy[v]); hz[v] = round_store<T>(hz[v]);
       }
 
+      const float4 hxv = pack(hx, T()), hyv = pack(hy, T()), hzv = pack(hz, T());
+      sX[tid] = hzv;
+      sX[NTc + tid] = hxv;
+      if (cfg.need_zfix) sX[2 * NTc + tid] = hyv;
+      ok = bar_compute_and(NTc, ok);               // B_i (+ uniform failure decision)
+      if (!ok) break;
       if (real) {
-        const float4 hxv = pack(hx, T()), hyv = pack(hy, T()), hzv = pack(hz, T());
-        sX[tid] = hzv;
-        sX[NTc + tid] = hxv;
-        if (cfg.need_zfix) sX[2 * NTc + tid] = hyv;
-        bar_compute(NTc);                          // B_i
         float hz_ym[VW], hx_ym[VW];
         const int nm = own ? tid - g.Zq : tid;
         unpack(sX[nm], hz_ym, T());
@@ -296,7 +425,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
               qsy[4 * v] = r.x; qsy[4 * v + 1] = r.y; qsy[4 * v + 2] = r.z; qsy[4 * v + 3] = r.w;
             }
           }
-          unpack(bb0, b0, T()); unpack(bb1, b1, T()); unpack(bb2, b2, T());
+          unpack(bC[tid], b0, T()); unpack(bC[NTc + tid], b1, T()); unpack(bC[2 * NTc + tid], b2, T());
           float ae[VW], be[VW], ike[VW];
           load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
 #pragma unroll
@@ -341,17 +470,20 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       for (int v = 0; v < VW; ++v) { hyp[v] = hy[v]; hzp[v] = hz[v]; }
     }
     cp_async_wait<0>();
-    __syncthreads();                               // end of sweep (pairs with the sync warp)
-    if (!s_ok) break;
+    bar_compute(NTc);                              // end of sweep: all stores issued, ring drained
+    iters_done += (unsigned)g.X + 1u;
+    if (tid == 0 && ok) st_release_cta(&ctl.done, base_mine + (unsigned)g.X);
   }
+  bar_compute(NTc);
+  if (tid == 0) st_release_cta(&ctl.exit_, 1u);
 }
 
 template <typename T, int D>
 size_t systolic2_smem_bytes(const Geom& g, int compute_threads, int tile_y) {
   constexpr int PV = VecTraits<T>::VW / 4;
   const size_t npsi = (size_t)(tile_y + 2) * g.npg * PV;
-  return sizeof(float4) * ((size_t)(D + 2) * 3 * compute_threads + (size_t)(D + 1) * 3 * compute_threads +
-                           3 * (size_t)compute_threads + (size_t)(D + 1) * 4 * npsi);
+  return sizeof(float4) * ((size_t)((D + 2) * 3 + 2 * (D + 1) * 3 + 3) * compute_threads +
+                           (size_t)(D + 1) * 4 * npsi);
 }
 
 template <typename T, int D>
@@ -361,6 +493,12 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
                                           : kSys2MaxCompute;
   if (g.Zq * 3 > max_threads) { *why = "z extent too large for one CTA"; return false; }
   int max_tile = max_threads / g.Zq - 2;
+  // largest tile whose staging ring fits in shared memory
+  while (max_tile >= 1 &&
+         systolic2_smem_bytes<T, D>(g, ((max_tile + 2) * g.Zq + 31) / 32 * 32, max_tile) + 64 >
+             227 * 1024)
+    --max_tile;
+  if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
   if (max_tile > g.Y) max_tile = g.Y;
   const int ntiles = (g.Y + max_tile - 1) / max_tile;
@@ -368,35 +506,42 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   const int compute = ((widest + 2) * g.Zq + 31) / 32 * 32;
   cfg->tile_y = widest;
   cfg->ntiles = ntiles;
-  cfg->threads = compute + 32;
+  cfg->threads = compute + kSys2Service;
   cfg->need_zfix = (32 % g.Zq != 0);
   cfg->smem_bytes = (int)systolic2_smem_bytes<T, D>(g, compute, widest);
-  // >= 2D+4 is needed for deadlock freedom (a throttled stage has published i-2 indices while
-  // its successor needs i'+D+2 of them to advance).
-  cfg->max_lead = 2 * D + 6;
+  // >= 2D+4 is needed for deadlock freedom (a throttled stage has published i-2 indices while its
+  // successor needs i'+D+2 of them to advance); the rest is slack for the
+  // polling/publishing latency.
+  cfg->max_lead = 2 * D + 8;
+  cfg->pf_ahead = 6;
+  // tuning knobs (benchmark sweeps only; values below the deadlock bound are clamped)
+  if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
+  if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
+  if (cfg->max_lead < 2 * D + 4) cfg->max_lead = 2 * D + 4;
+  if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
   int occ = 0;
-  if (cfg->smem_bytes > 227 * 1024 ||
-      cudaFuncSetAttribute(systolic2_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(systolic2_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            cfg->smem_bytes) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, systolic2_kernel<T, D>, cfg->threads,
                                                     cfg->smem_bytes) != cudaSuccess || occ < 1) {
     cudaGetLastError();
-    *why = "staging ring does not fit in shared memory";
+    *why = "kernel does not fit on an SM";
     return false;
   }
   const long long capacity = (long long)occ * sms;
   if (ntiles > capacity) { *why = "more y-tiles than co-resident CTAs"; return false; }
   int stages = (int)(capacity / ntiles);
   const long long plane_bytes = g.P * (long long)sizeof(T) * 15;
-  long long by_l2 = (long long)(l2_bytes * 0.5) / ((3 + D) * plane_bytes);
+  const int lag = D + 5;                         // planes a stage trails its predecessor by
+  long long by_l2 = (long long)(l2_bytes * 0.6) / (lag * plane_bytes);
   if (by_l2 < 1) by_l2 = 1;
   if (stages > by_l2) stages = (int)by_l2;
   if (stages_req > 0 && stages_req <= capacity / ntiles) stages = stages_req;
   if (stages > g.tt) stages = g.tt > 0 ? g.tt : 1;
   if (stages > g.X) stages = g.X;
   cfg->stages = stages;
-  cfg->l2_window_bytes = (long long)stages * (3 + D) * plane_bytes;
+  cfg->l2_window_bytes = (long long)stages * lag * plane_bytes;
   return true;
 }
 
