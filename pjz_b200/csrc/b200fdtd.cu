@@ -289,6 +289,11 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
   p.tab = reinterpret_cast<float*>(ws + w.tab);
   p.psiH[0] = psi; p.psiH[1] = psi + psi_n; p.psiE[0] = psi + 2 * psi_n; p.psiE[1] = psi + 3 * psi_n;
   p.psiH2[0] = psi + 4 * psi_n; p.psiH2[1] = psi + 5 * psi_n;   // carved only for the systolic kernel
+  for (int c = 0; c < 3; ++c) {
+    p.Es[0][c] = p.E[c]; p.Es[1][c] = p.E2[c];
+    p.Hs[0][c] = p.H[c]; p.Hs[1][c] = p.H2[c];
+  }
+  for (int c = 0; c < 2; ++c) { p.psiHs[0][c] = p.psiH[c]; p.psiHs[1][c] = p.psiH2[c]; }
   p.src = static_cast<const float*>(in[B200FDTD_IN_SOURCE_FIELD]);
   p.wave = static_cast<const float*>(in[B200FDTD_IN_SOURCE_WAVEFORM]);
   p.out = static_cast<float*>(out[0]);

@@ -40,6 +40,9 @@ struct Ptrs {
   const float* tab;    // [6][Zp]    a_e,b_e,ik_e,a_h,b_h,ik_h
   float* psiH[2];      // [X][Y][npg][VW]  (psiHx, psiHy), fp32 always
   float* psiH2[2];     // ping-pong copy (systolic kernel only)
+  T* Es[2][3];         // the same pointers indexed [buffer set][component] (constant-bank lookup)
+  T* Hs[2][3];
+  float* psiHs[2][2];
   float* psiE[2];
   const float* src;    // source_field, caller layout
   const float* wave;   // (tt,2)

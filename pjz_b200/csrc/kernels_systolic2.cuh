@@ -66,15 +66,15 @@ __device__ __forceinline__ bool bar_compute_and(int nthreads, bool pred) {
       : "=r"(r) : "r"(nthreads), "r"((int)pred) : "memory");
   return r != 0;
 }
-__device__ __forceinline__ unsigned ld_acquire_cta(const unsigned* smem_word) {
-  unsigned v;
-  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_word);
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
+// Shared-memory control words are accessed with volatile loads/stores: an acquire/release at
+// CTA scope costs a MEMBAR.ALL.CTA per access, and none is needed -- each consumer branches on
+// the loaded value before issuing its dependent memory operations, each producer's stored value
+// is data-dependent on the loads it summarises.
+__device__ __forceinline__ unsigned ld_vol_s(const unsigned* smem_word) {
+  return *reinterpret_cast<const volatile unsigned*>(smem_word);
 }
-__device__ __forceinline__ void st_release_cta(unsigned* smem_word, unsigned v) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_word);
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ void st_vol_s(unsigned* smem_word, unsigned v) {
+  *reinterpret_cast<volatile unsigned*>(smem_word) = v;
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -111,6 +111,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   float4* const sB = sH + (size_t)NH * 3 * NTc;              // [NH][3][NTc]
   float4* const sX = sB + (size_t)NH * 3 * NTc;              // [3][NTc]  Hz, Hx, Hy (new)
   float4* const sP = sX + (size_t)3 * NTc;                   // [NH][4][npsi]
+  float4* const sT = sP + (size_t)NH * 4 * npsi;             // [6][Zp/4] CPML tables
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
@@ -118,6 +119,8 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   if (tid == 0) {
     ctl.avail = 0; ctl.next = 0; ctl.done = 0; ctl.front = 0; ctl.ok = 1; ctl.exit_ = 0;
   }
+  for (int i = tid; i < 6 * g.Zp / 4; i += blockDim.x)
+    sT[i] = __ldg(reinterpret_cast<const float4*>(p.tab) + i);
   __syncthreads();
 
   // =================================== poller warp ===============================================
@@ -133,19 +136,19 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     const size_t pf_off = (size_t)ylo * g.Zp;
     unsigned pf_done = 0;                          // cumulative iterations already prefetched
     const unsigned sweep_iters = (unsigned)g.X + 1u;
-    while (ld_acquire_cta(&ctl.exit_) == 0) {
+    while (ld_vol_s(&ctl.exit_) == 0) {
       unsigned v = 0xffffffffu;
       if (lane < 5) v = ld_acquire_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
                      v4 = __shfl_sync(0xffffffffu, v, 4);
       if (lane == 0) {
-        st_release_cta(&ctl.avail, min(v0, min(v1, v2)));
-        st_release_cta(&ctl.next, v3);
-        if (v4 != 0) st_release_cta(&ctl.ok, 0u);
+        st_vol_s(&ctl.avail, min(v0, min(v1, v2)));
+        st_vol_s(&ctl.next, v3);
+        if (v4 != 0) st_vol_s(&ctl.ok, 0u);
       }
       // prefetch the planes of iterations [front + D, front + D + pf_ahead) into L2
-      const unsigned front = ld_acquire_cta(&ctl.front);
+      const unsigned front = ld_vol_s(&ctl.front);
       const unsigned want = front + (unsigned)D + (unsigned)cfg.pf_ahead;
       if (cfg.pf_ahead > 0 && lane >= 8 && lane < 17) {
         if (pf_done < front + (unsigned)D) pf_done = front + (unsigned)D;
@@ -174,8 +177,8 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     if (lane == 0) {
       unsigned last = 0;
       while (true) {
-        const unsigned ex = ld_acquire_cta(&ctl.exit_);
-        const unsigned d = ld_acquire_cta(&ctl.done);
+        const unsigned ex = ld_vol_s(&ctl.exit_);
+        const unsigned d = ld_vol_s(&ctl.done);
         if (d != last) {
           st_release_u32(my_prog, d);              // fence.acq_rel.gpu + store
           last = d;
@@ -190,123 +193,124 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   }
 
   // ================================= compute warps ===============================================
-  const int c = tid / g.Zq, q = tid - c * g.Zq;
+  // Everything that does not change along the sweep is computed here, once: the loop body below
+  // is issue-bound, so it carries running plane/slot indices and forms each global offset with
+  // a single 64-bit multiply-add per plane.
+  const int Zq = g.Zq, X = g.X;
+  const int c = tid / Zq, q = tid - c * Zq;
   const bool active = c < Yt + 2;
   const bool doH = c <= Yt;
   const bool own = c >= 1 && c <= Yt;
   const int y = wrapi(y0 - 1 + (active ? c : 0), g.Y);
-  const size_t coff = ((size_t)y * g.Zq + q) * VW;
+  const size_t coff = ((size_t)y * Zq + q) * VW;
   const int slot = psi_slot(g, q);
   const bool has_psi = slot >= 0;
+  const bool psiH_thr = has_psi && doH, psiE_thr = has_psi && own;
   const size_t poff = ((size_t)y * g.npg + (has_psi ? slot : 0)) * VW;
   const size_t pplane = (size_t)g.Y * g.npg * VW;
+  const size_t gP = (size_t)g.P;
   const int pidx = (c * g.npg + (has_psi ? slot : 0)) * PV;   // float4 index inside a psi slot
-  const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < g.Zq;
+  const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < Zq;
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
-  const bool top = q + 1 == g.Zq, bottom = q == 0;
-  const size_t XY = (size_t)g.X * g.Y;
+  const bool top = q + 1 == Zq, bottom = q == 0;
+  const size_t XY = (size_t)X * g.Y;
+  const int nbp = doH ? tid + Zq : tid;            // ring index of the y+1 neighbour
+  const int nbm = own ? tid - Zq : tid;            // ring index of the y-1 neighbour
+  const int eslot = 3 * NTc, pslot = 4 * npsi;     // float4 per ring slot
+  const int tstride = g.Zp / 4;
+  const float4* const tq = sT + q * PV;            // CPML table w of this z-group: tq[w*tstride + v]
+  // plane source: cheap pre-test so that add_source() is off the common path
+  const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : g.Y);
+  const bool src_thr = g.src_axis == 1 ? (y == sp0 || y == sp1)
+                                       : (g.src_axis == 2 && q == g.src_pos / VW);
   bool ok = true;
 
-  // CPML tables of this z-group are re-read from L1 (ld.global.nc, 3 KB total) where used:
-  // holding all six in registers would cost 6*VW registers for the whole kernel.
   auto load_tab = [&](int which, float (&dst)[VW]) {
 #pragma unroll
-    for (int v = 0; v < VW; v += 4) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(p.tab + which * g.Zp + q * VW + v));
-      dst[v] = r.x; dst[v + 1] = r.y; dst[v + 2] = r.z; dst[v + 3] = r.w;
+    for (int v = 0; v < PV; ++v) {
+      const float4 r = tq[which * tstride + v];
+      dst[4 * v] = r.x; dst[4 * v + 1] = r.y; dst[4 * v + 2] = r.z; dst[4 * v + 3] = r.w;
     }
   };
 
   unsigned iters_done = 0;                         // cumulative iterations finished (for front)
   for (int n = j; n < g.tt && ok; n += S) {
     const int m = n / S;
-    const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)g.X;
-    const unsigned base_mine = (unsigned)m * (unsigned)g.X;
+    const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)X;
+    const unsigned base_mine = (unsigned)m * (unsigned)X;
     const bool has_prev = n > 0, has_next = n + 1 < g.tt && j + 1 < S;
-    const int rb = n & 1;
-    const T* const Er0 = rb ? p.E2[0] : p.E[0];
-    const T* const Er1 = rb ? p.E2[1] : p.E[1];
-    const T* const Er2 = rb ? p.E2[2] : p.E[2];
-    const T* const Hr0 = rb ? p.H2[0] : p.H[0];
-    const T* const Hr1 = rb ? p.H2[1] : p.H[1];
-    const T* const Hr2 = rb ? p.H2[2] : p.H[2];
-    T* const Ew0 = rb ? p.E[0] : p.E2[0];
-    T* const Ew1 = rb ? p.E[1] : p.E2[1];
-    T* const Ew2 = rb ? p.E[2] : p.E2[2];
-    T* const Hw0 = rb ? p.H[0] : p.H2[0];
-    T* const Hw1 = rb ? p.H[1] : p.H2[1];
-    T* const Hw2 = rb ? p.H[2] : p.H2[2];
-    const float* const pHr0 = rb ? p.psiH2[0] : p.psiH[0];
-    const float* const pHr1 = rb ? p.psiH2[1] : p.psiH[1];
-    float* const pHw0 = rb ? p.psiH[0] : p.psiH2[0];
-    float* const pHw1 = rb ? p.psiH[1] : p.psiH2[1];
-    const int cstart = n % g.X;
+    const int rb = n & 1, wb = rb ^ 1;
+    const T* const Er0 = p.Es[rb][0]; const T* const Er1 = p.Es[rb][1]; const T* const Er2 = p.Es[rb][2];
+    const T* const Hr0 = p.Hs[rb][0]; const T* const Hr1 = p.Hs[rb][1]; const T* const Hr2 = p.Hs[rb][2];
+    const float* const pHr0 = p.psiHs[rb][0]; const float* const pHr1 = p.psiHs[rb][1];
+    const int cstart = n % X;
     const int oi = snapshot_index(g, n);
     const float w0 = __ldg(p.wave + 2 * (size_t)n), w1 = __ldg(p.wave + 2 * (size_t)n + 1);
 
     // Blocks until the loads of iteration `it` are allowed: they read planes up to sweep index
     // it+1 of the previous stage, which therefore must have finished it+2 indices on the tiles
     // t-1, t, t+1 (the k+3 rule); and they must not run more than max_lead indices ahead of the
-    // next stage (keeps the planes in flight inside L2).  Spins on shared memory only.
-    auto wait_deps = [&](int it) {
-      const unsigned need = base_prev + (unsigned)min(it + 2, g.X);
-      const int lead = min(it, g.X) - 1 - cfg.max_lead;
+    // next stage (keeps the planes in flight inside L2).  Spins on shared memory only; the
+    // branch on the loaded value orders the following loads behind it (no speculation on GPUs).
+    auto wait_deps = [&](int it) -> bool {
+      const unsigned need = base_prev + (unsigned)min(it + 2, X);
+      const int lead = min(it, X) - 1 - cfg.max_lead;
       const unsigned need_next = base_mine + (unsigned)max(lead, 0);
+      const bool chk_a = has_prev, chk_b = has_next && lead > 0;
+      if ((!chk_a || ld_vol_s(&ctl.avail) >= need) && (!chk_b || ld_vol_s(&ctl.next) >= need_next))
+        return true;
       unsigned long long t0 = 0;
       unsigned spins = 0;
       while (true) {
-        const bool a = !has_prev || ld_acquire_cta(&ctl.avail) >= need;
-        const bool b = !has_next || lead <= 0 || ld_acquire_cta(&ctl.next) >= need_next;
+        const bool a = !chk_a || ld_vol_s(&ctl.avail) >= need;
+        const bool b = !chk_b || ld_vol_s(&ctl.next) >= need_next;
         if (a && b) return true;
-        if (ld_acquire_cta(&ctl.ok) == 0) return false;
+        if (ld_vol_s(&ctl.ok) == 0) return false;
         if ((++spins & 255u) == 0) {
           const unsigned long long now = globaltimer_ns();
           if (t0 == 0) t0 = now;
           else if (now - t0 > 5000000000ull) {
             atomicCAS(status, 0u, 1u + blockIdx.x);
-            st_release_cta(&ctl.ok, 0u);
+            st_vol_s(&ctl.ok, 0u);
             return false;
           }
         }
       }
     };
 
-    // Issues the async copies that iteration `it` consumes: E[P_it + 1], H[P_it], B[P_it],
-    // psi[P_it] (+ E[P_0] for the very first one).  P_it = cstart - 1 + it.
-    auto issue = [&](int it) {
-      if (it <= g.X && active) {
-        const int P = wrapi(cstart - 1 + it, g.X);
-        const int Pn = wrapi(P + 1, g.X);
-        const size_t offP = (size_t)P * g.P + coff, offN = (size_t)Pn * g.P + coff;
-        float4* e = sE + (size_t)((it + 1) % NE) * 3 * NTc + tid;
+    // Async copies consumed by one iteration: E[Pn] -> E slot `se`, H/B/psi[P] -> slot `sh`.
+    auto issue = [&](int P, int Pn, int se, int sh, bool first, bool ecoef) {
+      if (active) {
+        const size_t offP = (size_t)P * gP + coff, offN = (size_t)Pn * gP + coff;
+        float4* e = sE + se * eslot + tid;
         cp_async16(e, Er0 + offN);
         cp_async16(e + 2 * NTc, Er2 + offN);
         if (doH) cp_async16(e + NTc, Er1 + offN);
-        if (it == 0) {
-          float4* e0 = sE + tid;                   // slot 0
+        if (first) {                               // very first plane of the sweep: E[P] too
+          float4* e0 = sE + tid;
           cp_async16(e0, Er0 + offP);
           cp_async16(e0 + 2 * NTc, Er2 + offP);
           if (doH) cp_async16(e0 + NTc, Er1 + offP);
         }
         if (doH) {
-          float4* h = sH + (size_t)(it % NH) * 3 * NTc + tid;
+          float4* h = sH + sh * eslot + tid;
           cp_async16(h, Hr0 + offP);
           cp_async16(h + NTc, Hr1 + offP);
           cp_async16(h + 2 * NTc, Hr2 + offP);
-          if (own && it >= 1) {
-            float4* b = sB + (size_t)(it % NH) * 3 * NTc + tid;
+          if (own && ecoef) {
+            float4* b = sB + sh * eslot + tid;
             cp_async16(b, p.B[0] + offP);
             cp_async16(b + NTc, p.B[1] + offP);
             cp_async16(b + 2 * NTc, p.B[2] + offP);
           }
           if (has_psi) {
-            float4* ps = sP + (size_t)(it % NH) * 4 * npsi + pidx;
+            float4* ps = sP + sh * pslot + pidx;
             const size_t po = (size_t)P * pplane + poff;
 #pragma unroll
             for (int v = 0; v < PV; ++v) {
               cp_async16(ps + v, pHr0 + po + 4 * v);
               cp_async16(ps + npsi + v, pHr1 + po + 4 * v);
-              if (own && it >= 1) {
+              if (own && ecoef) {
                 cp_async16(ps + 2 * npsi + v, p.psiE[0] + po + 4 * v);
                 cp_async16(ps + 3 * npsi + v, p.psiE[1] + po + 4 * v);
               }
@@ -314,15 +318,19 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
           }
         }
       }
-      cp_async_commit();
     };
 
-    // A failed wait (timeout / another CTA gave up) is turned into a CTA-uniform decision at the
-    // next AND-reducing barrier, so all compute threads leave the loops at the same point.
+    // ---- fill the ring: iterations 0 .. D-1 ------------------------------------------------------
+    // A failed wait (timeout / another CTA gave up) becomes a CTA-uniform decision at the next
+    // AND-reducing barrier, so all compute threads leave the loops at the same point.
+    int PL = wrapi(cstart - 1, X);                 // plane whose H/B/psi the next issue() loads
 #pragma unroll
     for (int it = 0; it < D; ++it) {
       ok = ok && wait_deps(it);
-      if (ok) issue(it); else cp_async_commit();
+      const int PLn = PL + 1 == X ? 0 : PL + 1;
+      if (ok && it <= X) issue(PL, PLn, it + 1, it, it == 0, it >= 1);
+      cp_async_commit();
+      PL = PLn;
     }
     ok = bar_compute_and(NTc, ok);
 
@@ -330,67 +338,87 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 #pragma unroll
     for (int v = 0; v < VW; ++v) { hyp[v] = 0.f; hzp[v] = 0.f; }
     float a0n = 0.f, a1n = 0.f, a2n = 0.f;       // absorber row of the NEXT plane (prefetched)
+    int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
+    int se = 0, sh = 0;                            // ring slots of E[P] and H/B/psi[P]
 
-    for (int i = 0; i <= g.X && ok; ++i) {         // i = 0 is the prologue plane cstart-1
-      const int P = wrapi(cstart - 1 + i, g.X);
-      const size_t offP = (size_t)P * g.P + coff;
+    for (int i = 0; i <= X && ok; ++i) {
       const bool real = i >= 1;
+      const int Pn = P + 1 == X ? 0 : P + 1;
+      const int sen = se + 1 == NE ? 0 : se + 1;   // slot of E[P+1]
       cp_async_wait<D - 1>();
       bar_compute(NTc);                            // A_i
       if (tid == 0) {
         // every store of iterations < i has been issued by all compute threads
-        if (i >= 2) st_release_cta(&ctl.done, base_mine + (unsigned)(i - 1));
-        st_release_cta(&ctl.front, iters_done + (unsigned)i);
+        if (i >= 2) st_vol_s(&ctl.done, base_mine + (unsigned)(i - 1));
+        st_vol_s(&ctl.front, iters_done + (unsigned)i);
       }
       ok = wait_deps(i + D);
-      if (ok) issue(i + D); else cp_async_commit();
+      {
+        const int PLn = PL + 1 == X ? 0 : PL + 1;
+        // loads of iteration i+D go to the slots freed by iteration i-1
+        if (ok && i + D <= X)
+          issue(PL, PLn, se == 0 ? NE - 1 : se - 1, sh == 0 ? NH - 1 : sh - 1, false, true);
+        cp_async_commit();
+        PL = PLn;
+      }
 
       const float a0 = a0n, a1 = a1n, a2 = a2n;
-      if (own && i < g.X) {
-        const size_t xy = (size_t)wrapi(P + 1, g.X) * g.Y + y;
+      if (own && i < X) {
+        const size_t xy = (size_t)Pn * g.Y + y;
         a0n = __ldg(p.A + xy); a1n = __ldg(p.A + XY + xy); a2n = __ldg(p.A + 2 * XY + xy);
       }
-      const float4* eC = sE + (size_t)(i % NE) * 3 * NTc;         // E^n[P]
-      const float4* eN = sE + (size_t)((i + 1) % NE) * 3 * NTc;   // E^n[P+1]
-      const float4* hO = sH + (size_t)(i % NH) * 3 * NTc;         // H^{n-1/2}[P]
-      const float4* bC = sB + (size_t)(i % NH) * 3 * NTc;         // B[P]
-      const float4* pS = sP + (size_t)(i % NH) * 4 * npsi + pidx;
+      const float4* eC = sE + se * eslot;          // E^n[P]
+      const float4* eN = sE + sen * eslot;         // E^n[P+1]
+      const float4* hO = sH + sh * eslot;          // H^{n-1/2}[P]
+      const float4* bC = sB + sh * eslot;          // B[P]
+      const float4* pS = sP + sh * pslot + pidx;
 
-      float ex[VW], ey[VW], ez[VW], ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW];
-      float hx[VW], hy[VW], hz[VW], psx[VW], psy[VW];
-      const int nb = doH ? tid + g.Zq : tid;
-      unpack(eC[tid], ex, T()); unpack(eC[NTc + tid], ey, T()); unpack(eC[2 * NTc + tid], ez, T());
-      unpack(eC[2 * NTc + nb], ez_yp, T()); unpack(eC[nb], ex_yp, T());
-      unpack(eN[NTc + tid], ey_xp, T()); unpack(eN[2 * NTc + tid], ez_xp, T());
-      unpack(hO[tid], hx, T()); unpack(hO[NTc + tid], hy, T()); unpack(hO[2 * NTc + tid], hz, T());
+      float ex[VW], ey[VW], ez[VW], hx[VW], hy[VW], hz[VW];
+      {
+        float ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW], psx[VW], psy[VW];
+        unpack(eC[tid], ex, T()); unpack(eC[NTc + tid], ey, T()); unpack(eC[2 * NTc + tid], ez, T());
+        unpack(eC[2 * NTc + nbp], ez_yp, T()); unpack(eC[nbp], ex_yp, T());
+        unpack(eN[NTc + tid], ey_xp, T()); unpack(eN[2 * NTc + tid], ez_xp, T());
+        unpack(hO[tid], hx, T()); unpack(hO[NTc + tid], hy, T()); unpack(hO[2 * NTc + tid], hz, T());
 #pragma unroll
-      for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
-      if (has_psi && doH) {
+        for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
+        if (psiH_thr) {
 #pragma unroll
-        for (int v = 0; v < PV; ++v) {
-          float4 r = pS[v];
-          psx[4 * v] = r.x; psx[4 * v + 1] = r.y; psx[4 * v + 2] = r.z; psx[4 * v + 3] = r.w;
-          r = pS[npsi + v];
-          psy[4 * v] = r.x; psy[4 * v + 1] = r.y; psy[4 * v + 2] = r.z; psy[4 * v + 3] = r.w;
+          for (int v = 0; v < PV; ++v) {
+            float4 r = pS[v];
+            psx[4 * v] = r.x; psx[4 * v + 1] = r.y; psx[4 * v + 2] = r.z; psx[4 * v + 3] = r.w;
+            r = pS[npsi + v];
+            psy[4 * v] = r.x; psy[4 * v + 1] = r.y; psy[4 * v + 2] = r.z; psy[4 * v + 3] = r.w;
+          }
         }
-      }
-      float ah[VW], bh[VW], ikh[VW];
-      load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
-      float ex_top = __shfl_down_sync(0xffffffffu, ex[0], 1);
-      float ey_top = __shfl_down_sync(0xffffffffu, ey[0], 1);
-      if (fix_up) {
-        float tmp[VW];
-        unpack(eC[tid + 1], tmp, T()); ex_top = tmp[0];
-        unpack(eC[NTc + tid + 1], tmp, T()); ey_top = tmp[0];
-      }
-      if (top) { ex_top = 0.f; ey_top = 0.f; }
+        float ah[VW], bh[VW], ikh[VW];
+        load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
+        float ex_top = __shfl_down_sync(0xffffffffu, ex[0], 1);
+        float ey_top = __shfl_down_sync(0xffffffffu, ey[0], 1);
+        if (fix_up) {
+          float tmp[VW];
+          unpack(eC[tid + 1], tmp, T()); ex_top = tmp[0];
+          unpack(eC[NTc + tid + 1], tmp, T()); ey_top = tmp[0];
+        }
+        if (top) { ex_top = 0.f; ey_top = 0.f; }
 #pragma unroll
-      for (int v = 0; v < VW; ++v) {
-        const float exz = (v + 1 < VW) ? ex[(v + 1) % VW] : ex_top;
-        const float eyz = (v + 1 < VW) ? ey[(v + 1) % VW] : ey_top;
-        h_cell(ex[v], ey[v], ez[v], exz, eyz, ez_yp[v], ex_yp[v], ey_xp[v], ez_xp[v], ah[v], bh[v],
-               ikh[v], g.dt, psx[v], psy[v], hx[v], hy[v], hz[v]);
-        hx[v] = round_store<T>(hx[v]); hy[v] = round_store<T>(hy[v]); hz[v] = round_store<T>(hz[v]);
+        for (int v = 0; v < VW; ++v) {
+          const float exz = (v + 1 < VW) ? ex[(v + 1) % VW] : ex_top;
+          const float eyz = (v + 1 < VW) ? ey[(v + 1) % VW] : ey_top;
+          h_cell(ex[v], ey[v], ez[v], exz, eyz, ez_yp[v], ex_yp[v], ey_xp[v], ez_xp[v], ah[v], bh[v],
+                 ikh[v], g.dt, psx[v], psy[v], hx[v], hy[v], hz[v]);
+          hx[v] = round_store<T>(hx[v]); hy[v] = round_store<T>(hy[v]); hz[v] = round_store<T>(hz[v]);
+        }
+        if (psiH_thr && own && real) {             // new psiH of the owned PML cells
+          const size_t po = (size_t)P * pplane + poff;
+          float* const w0p = p.psiHs[wb][0] + po;
+          float* const w1p = p.psiHs[wb][1] + po;
+#pragma unroll
+          for (int v = 0; v < VW; v += 4) {
+            __stcg(reinterpret_cast<float4*>(w0p + v), make_float4(psx[v], psx[v + 1], psx[v + 2], psx[v + 3]));
+            __stcg(reinterpret_cast<float4*>(w1p + v), make_float4(psy[v], psy[v + 1], psy[v + 2], psy[v + 3]));
+          }
+        }
       }
 
       const float4 hxv = pack(hx, T()), hyv = pack(hy, T()), hzv = pack(hz, T());
@@ -400,10 +428,6 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       ok = bar_compute_and(NTc, ok);               // B_i (+ uniform failure decision)
       if (!ok) break;
       if (real) {
-        float hz_ym[VW], hx_ym[VW];
-        const int nm = own ? tid - g.Zq : tid;
-        unpack(sX[nm], hz_ym, T());
-        unpack(sX[NTc + nm], hx_ym, T());
         float hx_bot = __shfl_up_sync(0xffffffffu, hx[VW - 1], 1);
         float hy_bot = __shfl_up_sync(0xffffffffu, hy[VW - 1], 1);
         if (fix_dn) {
@@ -413,10 +437,13 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         }
         if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
         if (own) {
-          float qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
+          const size_t offP = (size_t)P * gP + coff;
+          float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
+          unpack(sX[nbm], hz_ym, T());
+          unpack(sX[NTc + nbm], hx_ym, T());
 #pragma unroll
           for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
-          if (has_psi) {
+          if (psiE_thr) {
 #pragma unroll
             for (int v = 0; v < PV; ++v) {
               float4 r = pS[2 * npsi + v];
@@ -435,21 +462,18 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             e_cell(hx[v], hy[v], hz[v], hxz, hyz, hz_ym[v], hx_ym[v], hyp[v], hzp[v], ae[v], be[v],
                    ike[v], a0, a1, a2, b0[v], b1[v], b2[v], qsx[v], qsy[v], ex[v], ey[v], ez[v]);
           }
-          add_source<VW>(g, p.src, w0, w1, P, y, q, ex, ey, ez);
-          st16<LD_CG>(Hw0 + offP, hxv);
-          st16<LD_CG>(Hw1 + offP, hyv);
-          st16<LD_CG>(Hw2 + offP, hzv);
-          store_vec<T, LD_CG>(Ew0 + offP, ex);
-          store_vec<T, LD_CG>(Ew1 + offP, ey);
-          store_vec<T, LD_CG>(Ew2 + offP, ez);
-          if (has_psi) {
+          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : src_thr)
+            add_source<VW>(g, p.src, w0, w1, P, y, q, ex, ey, ez);
+          st16<LD_CG>(p.Hs[wb][0] + offP, hxv);
+          st16<LD_CG>(p.Hs[wb][1] + offP, hyv);
+          st16<LD_CG>(p.Hs[wb][2] + offP, hzv);
+          store_vec<T, LD_CG>(p.Es[wb][0] + offP, ex);
+          store_vec<T, LD_CG>(p.Es[wb][1] + offP, ey);
+          store_vec<T, LD_CG>(p.Es[wb][2] + offP, ez);
+          if (psiE_thr) {
             const size_t po = (size_t)P * pplane + poff;
 #pragma unroll
             for (int v = 0; v < VW; v += 4) {
-              __stcg(reinterpret_cast<float4*>(pHw0 + po + v),
-                     make_float4(psx[v], psx[v + 1], psx[v + 2], psx[v + 3]));
-              __stcg(reinterpret_cast<float4*>(pHw1 + po + v),
-                     make_float4(psy[v], psy[v + 1], psy[v + 2], psy[v + 3]));
               __stcg(reinterpret_cast<float4*>(p.psiE[0] + po + v),
                      make_float4(qsx[v], qsx[v + 1], qsx[v + 2], qsx[v + 3]));
               __stcg(reinterpret_cast<float4*>(p.psiE[1] + po + v),
@@ -468,14 +492,17 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       }
 #pragma unroll
       for (int v = 0; v < VW; ++v) { hyp[v] = hy[v]; hzp[v] = hz[v]; }
+      P = Pn;
+      se = sen;
+      sh = sh + 1 == NH ? 0 : sh + 1;
     }
     cp_async_wait<0>();
     bar_compute(NTc);                              // end of sweep: all stores issued, ring drained
-    iters_done += (unsigned)g.X + 1u;
-    if (tid == 0 && ok) st_release_cta(&ctl.done, base_mine + (unsigned)g.X);
+    iters_done += (unsigned)X + 1u;
+    if (tid == 0 && ok) st_vol_s(&ctl.done, base_mine + (unsigned)X);
   }
   bar_compute(NTc);
-  if (tid == 0) st_release_cta(&ctl.exit_, 1u);
+  if (tid == 0) st_vol_s(&ctl.exit_, 1u);
 }
 
 template <typename T, int D>
@@ -483,7 +510,7 @@ size_t systolic2_smem_bytes(const Geom& g, int compute_threads, int tile_y) {
   constexpr int PV = VecTraits<T>::VW / 4;
   const size_t npsi = (size_t)(tile_y + 2) * g.npg * PV;
   return sizeof(float4) * ((size_t)((D + 2) * 3 + 2 * (D + 1) * 3 + 3) * compute_threads +
-                           (size_t)(D + 1) * 4 * npsi);
+                           (size_t)(D + 1) * 4 * npsi + 6 * (size_t)g.Zp / 4);
 }
 
 template <typename T, int D>
