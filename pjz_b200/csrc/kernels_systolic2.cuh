@@ -24,8 +24,11 @@
 //  * Two compute-only CTA barriers per plane: (A) "ring slot landed, previous iteration's
 //    shared-memory reads done", (B) exchange of the freshly formed H for the y-1/z-1 neighbours.
 //
-// Register budget: registers are partitioned per SM sub-partition, so at most 16 warps can hold
-// more than 96 registers each; the CTA is therefore capped at 14 compute + 2 service warps.
+//  * Two adjacent columns per thread: the y+1 neighbour of the even column and the y-1
+//    neighbour of the odd one are the thread's own registers, CPML tables / dependency checks /
+//    loop bookkeeping are shared, and only 8 compute warps meet at the barriers.
+//
+// Register budget: 8 compute + 2 service warps leave ~200 registers per thread.
 #pragma once
 
 #include <stdio.h>
@@ -38,7 +41,7 @@
 
 namespace b200 {
 
-constexpr int kSys2MaxCompute = 448;   // 14 warps
+constexpr int kSys2MaxCompute = 256;   // 8 warps, two columns per thread
 constexpr int kSys2Service = 64;       // poller warp + publisher warp
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -76,6 +79,14 @@ __device__ __forceinline__ unsigned ld_vol_s(const unsigned* smem_word) {
 __device__ __forceinline__ void st_vol_s(unsigned* smem_word, unsigned v) {
   *reinterpret_cast<volatile unsigned*>(smem_word) = v;
 }
+// Progress counters are polled with a relaxed gpu-scope load (served by L2, the point of
+// coherence).  ld.acquire.gpu would add a CCTL.IVALL (L1 invalidate) per poll; the data loads
+// that depend on the counter bypass L1 (cp.async.cg) and are issued behind a branch on its value.
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
@@ -105,13 +116,15 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const int y0 = (int)((long long)t * g.Y / NT);
   const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
   const int npsi = (cfg.tile_y + 2) * g.npg * PV; // float4 per psi array per slot
+  const int ring = (cfg.tile_y + 2) * g.Zq;       // float4 per component per ring slot
+  const int eslot = 3 * ring, pslot = 4 * npsi;   // float4 per E/H/B slot, per psi slot
 
-  float4* const sE = smem;                                   // [NE][3][NTc]
-  float4* const sH = sE + (size_t)NE * 3 * NTc;              // [NH][3][NTc]
-  float4* const sB = sH + (size_t)NH * 3 * NTc;              // [NH][3][NTc]
-  float4* const sX = sB + (size_t)NH * 3 * NTc;              // [3][NTc]  Hz, Hx, Hy (new)
-  float4* const sP = sX + (size_t)3 * NTc;                   // [NH][4][npsi]
-  float4* const sT = sP + (size_t)NH * 4 * npsi;             // [6][Zp/4] CPML tables
+  float4* const sE = smem;                                   // [NE][3][ring]
+  float4* const sH = sE + (size_t)NE * eslot;                // [NH][3][ring]
+  float4* const sB = sH + (size_t)NH * eslot;                // [NH][3][ring]
+  float4* const sX = sB + (size_t)NH * eslot;                // [2 | 5][NTc] new H at pair boundaries
+  float4* const sP = sX + (size_t)(cfg.need_zfix ? 5 : 2) * NTc;   // [NH][4][npsi]
+  float4* const sT = sP + (size_t)NH * pslot;                // [6][Zp/4] CPML tables
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
@@ -138,7 +151,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     const unsigned sweep_iters = (unsigned)g.X + 1u;
     while (ld_vol_s(&ctl.exit_) == 0) {
       unsigned v = 0xffffffffu;
-      if (lane < 5) v = ld_acquire_u32(watch);
+      if (lane < 5) v = ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
                      v4 = __shfl_sync(0xffffffffu, v, 4);
@@ -168,7 +181,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         }
       }
       pf_done = __shfl_sync(0xffffffffu, pf_done, 8);
-      __nanosleep(100);
+      __nanosleep(200);
     }
     return;
   }
@@ -185,7 +198,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         } else if (ex) {
           break;
         } else {
-          __nanosleep(50);
+          __nanosleep(200);
         }
       }
     }
@@ -193,36 +206,44 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   }
 
   // ================================= compute warps ===============================================
-  // Everything that does not change along the sweep is computed here, once: the loop body below
-  // is issue-bound, so it carries running plane/slot indices and forms each global offset with
-  // a single 64-bit multiply-add per plane.
+  // One thread owns the 16-byte z-vector q of TWO adjacent columns (2cp, 2cp+1) of the loaded
+  // tile (columns 0 .. Yt+1 = y0-1 .. y0+Yt).  The y+1 neighbour of the even column and the y-1
+  // neighbour of the odd column are the thread's own registers; only the pair boundary goes
+  // through shared memory.  Everything that does not change along the sweep is computed here,
+  // once: the loop body is issue-bound.
   const int Zq = g.Zq, X = g.X;
-  const int c = tid / Zq, q = tid - c * Zq;
-  const bool active = c < Yt + 2;
-  const bool doH = c <= Yt;
-  const bool own = c >= 1 && c <= Yt;
-  const int y = wrapi(y0 - 1 + (active ? c : 0), g.Y);
-  const size_t coff = ((size_t)y * Zq + q) * VW;
+  const int cp = tid / Zq, q = tid - cp * Zq;
+  const int ncols = Yt + 2;
+  int f[2], yk[2];
+  bool act[2], doH[2], own[2];
+  size_t coff[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c = 2 * cp + k;
+    act[k] = c < ncols;
+    doH[k] = c <= Yt;
+    own[k] = c >= 1 && c <= Yt;
+    yk[k] = wrapi(y0 - 1 + (act[k] ? c : 0), g.Y);
+    f[k] = act[k] ? c * Zq + q : q;                // ring index of the item (in range if idle)
+    coff[k] = ((size_t)yk[k] * Zq + q) * VW;
+  }
   const int slot = psi_slot(g, q);
   const bool has_psi = slot >= 0;
-  const bool psiH_thr = has_psi && doH, psiE_thr = has_psi && own;
-  const size_t poff = ((size_t)y * g.npg + (has_psi ? slot : 0)) * VW;
   const size_t pplane = (size_t)g.Y * g.npg * VW;
   const size_t gP = (size_t)g.P;
-  const int pidx = (c * g.npg + (has_psi ? slot : 0)) * PV;   // float4 index inside a psi slot
   const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < Zq;
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
   const bool top = q + 1 == Zq, bottom = q == 0;
   const size_t XY = (size_t)X * g.Y;
-  const int nbp = doH ? tid + Zq : tid;            // ring index of the y+1 neighbour
-  const int nbm = own ? tid - Zq : tid;            // ring index of the y-1 neighbour
-  const int eslot = 3 * NTc, pslot = 4 * npsi;     // float4 per ring slot
   const int tstride = g.Zp / 4;
   const float4* const tq = sT + q * PV;            // CPML table w of this z-group: tq[w*tstride + v]
   // plane source: cheap pre-test so that add_source() is off the common path
   const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : g.Y);
-  const bool src_thr = g.src_axis == 1 ? (y == sp0 || y == sp1)
-                                       : (g.src_axis == 2 && q == g.src_pos / VW);
+  bool src_thr[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    src_thr[k] = g.src_axis == 1 ? (yk[k] == sp0 || yk[k] == sp1)
+                                 : (g.src_axis == 2 && q == g.src_pos / VW);
   bool ok = true;
 
   auto load_tab = [&](int which, float (&dst)[VW]) {
@@ -232,6 +253,18 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       dst[4 * v] = r.x; dst[4 * v + 1] = r.y; dst[4 * v + 2] = r.z; dst[4 * v + 3] = r.w;
     }
   };
+  auto load_psi = [&](const float4* ps, float (&dst)[VW]) {
+#pragma unroll
+    for (int v = 0; v < PV; ++v) {
+      const float4 r = ps[v];
+      dst[4 * v] = r.x; dst[4 * v + 1] = r.y; dst[4 * v + 2] = r.z; dst[4 * v + 3] = r.w;
+    }
+  };
+  auto store_psi = [&](float* dst, const float (&src)[VW]) {
+#pragma unroll
+    for (int v = 0; v < VW; v += 4)
+      __stcg(reinterpret_cast<float4*>(dst + v), make_float4(src[v], src[v + 1], src[v + 2], src[v + 3]));
+  };
 
   unsigned iters_done = 0;                         // cumulative iterations finished (for front)
   for (int n = j; n < g.tt && ok; n += S) {
@@ -240,9 +273,6 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     const unsigned base_mine = (unsigned)m * (unsigned)X;
     const bool has_prev = n > 0, has_next = n + 1 < g.tt && j + 1 < S;
     const int rb = n & 1, wb = rb ^ 1;
-    const T* const Er0 = p.Es[rb][0]; const T* const Er1 = p.Es[rb][1]; const T* const Er2 = p.Es[rb][2];
-    const T* const Hr0 = p.Hs[rb][0]; const T* const Hr1 = p.Hs[rb][1]; const T* const Hr2 = p.Hs[rb][2];
-    const float* const pHr0 = p.psiHs[rb][0]; const float* const pHr1 = p.psiHs[rb][1];
     const int cstart = n % X;
     const int oi = snapshot_index(g, n);
     const float w0 = __ldg(p.wave + 2 * (size_t)n), w1 = __ldg(p.wave + 2 * (size_t)n + 1);
@@ -253,18 +283,14 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     // next stage (keeps the planes in flight inside L2).  Spins on shared memory only; the
     // branch on the loaded value orders the following loads behind it (no speculation on GPUs).
     auto wait_deps = [&](int it) -> bool {
-      const unsigned need = base_prev + (unsigned)min(it + 2, X);
+      const unsigned need = has_prev ? base_prev + (unsigned)min(it + 2, X) : 0u;
       const int lead = min(it, X) - 1 - cfg.max_lead;
-      const unsigned need_next = base_mine + (unsigned)max(lead, 0);
-      const bool chk_a = has_prev, chk_b = has_next && lead > 0;
-      if ((!chk_a || ld_vol_s(&ctl.avail) >= need) && (!chk_b || ld_vol_s(&ctl.next) >= need_next))
-        return true;
+      const unsigned need_next = (has_next && lead > 0) ? base_mine + (unsigned)lead : 0u;
+      if (ld_vol_s(&ctl.avail) >= need && ld_vol_s(&ctl.next) >= need_next) return true;
       unsigned long long t0 = 0;
       unsigned spins = 0;
       while (true) {
-        const bool a = !chk_a || ld_vol_s(&ctl.avail) >= need;
-        const bool b = !chk_b || ld_vol_s(&ctl.next) >= need_next;
-        if (a && b) return true;
+        if (ld_vol_s(&ctl.avail) >= need && ld_vol_s(&ctl.next) >= need_next) return true;
         if (ld_vol_s(&ctl.ok) == 0) return false;
         if ((++spins & 255u) == 0) {
           const unsigned long long now = globaltimer_ns();
@@ -280,37 +306,39 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 
     // Async copies consumed by one iteration: E[Pn] -> E slot `se`, H/B/psi[P] -> slot `sh`.
     auto issue = [&](int P, int Pn, int se, int sh, bool first, bool ecoef) {
-      if (active) {
-        const size_t offP = (size_t)P * gP + coff, offN = (size_t)Pn * gP + coff;
-        float4* e = sE + se * eslot + tid;
-        cp_async16(e, Er0 + offN);
-        cp_async16(e + 2 * NTc, Er2 + offN);
-        if (doH) cp_async16(e + NTc, Er1 + offN);
+      const size_t pP = (size_t)P * gP, pN = (size_t)Pn * gP;
+      float4* const eb = sE + se * eslot;
+      float4* const hb = sH + sh * eslot;
+      float4* const bb = sB + sh * eslot;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!act[k]) continue;
+        const size_t offP = pP + coff[k], offN = pN + coff[k];
+        cp_async16(eb + f[k], p.Es[rb][0] + offN);
+        cp_async16(eb + 2 * ring + f[k], p.Es[rb][2] + offN);
+        if (doH[k]) cp_async16(eb + ring + f[k], p.Es[rb][1] + offN);
         if (first) {                               // very first plane of the sweep: E[P] too
-          float4* e0 = sE + tid;
-          cp_async16(e0, Er0 + offP);
-          cp_async16(e0 + 2 * NTc, Er2 + offP);
-          if (doH) cp_async16(e0 + NTc, Er1 + offP);
+          cp_async16(sE + f[k], p.Es[rb][0] + offP);
+          cp_async16(sE + 2 * ring + f[k], p.Es[rb][2] + offP);
+          if (doH[k]) cp_async16(sE + ring + f[k], p.Es[rb][1] + offP);
         }
-        if (doH) {
-          float4* h = sH + sh * eslot + tid;
-          cp_async16(h, Hr0 + offP);
-          cp_async16(h + NTc, Hr1 + offP);
-          cp_async16(h + 2 * NTc, Hr2 + offP);
-          if (own && ecoef) {
-            float4* b = sB + sh * eslot + tid;
-            cp_async16(b, p.B[0] + offP);
-            cp_async16(b + NTc, p.B[1] + offP);
-            cp_async16(b + 2 * NTc, p.B[2] + offP);
+        if (doH[k]) {
+          cp_async16(hb + f[k], p.Hs[rb][0] + offP);
+          cp_async16(hb + ring + f[k], p.Hs[rb][1] + offP);
+          cp_async16(hb + 2 * ring + f[k], p.Hs[rb][2] + offP);
+          if (own[k] && ecoef) {
+            cp_async16(bb + f[k], p.B[0] + offP);
+            cp_async16(bb + ring + f[k], p.B[1] + offP);
+            cp_async16(bb + 2 * ring + f[k], p.B[2] + offP);
           }
           if (has_psi) {
-            float4* ps = sP + sh * pslot + pidx;
-            const size_t po = (size_t)P * pplane + poff;
+            float4* ps = sP + sh * pslot + ((2 * cp + k) * g.npg + slot) * PV;
+            const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
 #pragma unroll
             for (int v = 0; v < PV; ++v) {
-              cp_async16(ps + v, pHr0 + po + 4 * v);
-              cp_async16(ps + npsi + v, pHr1 + po + 4 * v);
-              if (own && ecoef) {
+              cp_async16(ps + v, p.psiHs[rb][0] + po + 4 * v);
+              cp_async16(ps + npsi + v, p.psiHs[rb][1] + po + 4 * v);
+              if (own[k] && ecoef) {
                 cp_async16(ps + 2 * npsi + v, p.psiE[0] + po + 4 * v);
                 cp_async16(ps + 3 * npsi + v, p.psiE[1] + po + 4 * v);
               }
@@ -334,10 +362,12 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     }
     ok = bar_compute_and(NTc, ok);
 
-    float hyp[VW], hzp[VW];
+    float hyp[2][VW], hzp[2][VW];                  // H^{n+1/2}[P-1] of the thread's own cells
 #pragma unroll
-    for (int v = 0; v < VW; ++v) { hyp[v] = 0.f; hzp[v] = 0.f; }
-    float a0n = 0.f, a1n = 0.f, a2n = 0.f;       // absorber row of the NEXT plane (prefetched)
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int v = 0; v < VW; ++v) { hyp[k][v] = 0.f; hzp[k][v] = 0.f; }
+    float an[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // absorber rows of the NEXT plane
     int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
     int se = 0, sh = 0;                            // ring slots of E[P] and H/B/psi[P]
 
@@ -362,136 +392,147 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         PL = PLn;
       }
 
-      const float a0 = a0n, a1 = a1n, a2 = a2n;
-      if (own && i < X) {
-        const size_t xy = (size_t)Pn * g.Y + y;
-        a0n = __ldg(p.A + xy); a1n = __ldg(p.A + XY + xy); a2n = __ldg(p.A + 2 * XY + xy);
-      }
-      const float4* eC = sE + se * eslot;          // E^n[P]
-      const float4* eN = sE + sen * eslot;         // E^n[P+1]
-      const float4* hO = sH + sh * eslot;          // H^{n-1/2}[P]
-      const float4* bC = sB + sh * eslot;          // B[P]
-      const float4* pS = sP + sh * pslot + pidx;
-
-      float ex[VW], ey[VW], ez[VW], hx[VW], hy[VW], hz[VW];
-      {
-        float ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW], psx[VW], psy[VW];
-        unpack(eC[tid], ex, T()); unpack(eC[NTc + tid], ey, T()); unpack(eC[2 * NTc + tid], ez, T());
-        unpack(eC[2 * NTc + nbp], ez_yp, T()); unpack(eC[nbp], ex_yp, T());
-        unpack(eN[NTc + tid], ey_xp, T()); unpack(eN[2 * NTc + tid], ez_xp, T());
-        unpack(hO[tid], hx, T()); unpack(hO[NTc + tid], hy, T()); unpack(hO[2 * NTc + tid], hz, T());
+      float a[2][3];
 #pragma unroll
-        for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
-        if (psiH_thr) {
-#pragma unroll
-          for (int v = 0; v < PV; ++v) {
-            float4 r = pS[v];
-            psx[4 * v] = r.x; psx[4 * v + 1] = r.y; psx[4 * v + 2] = r.z; psx[4 * v + 3] = r.w;
-            r = pS[npsi + v];
-            psy[4 * v] = r.x; psy[4 * v + 1] = r.y; psy[4 * v + 2] = r.z; psy[4 * v + 3] = r.w;
-          }
+      for (int k = 0; k < 2; ++k) {
+        a[k][0] = an[k][0]; a[k][1] = an[k][1]; a[k][2] = an[k][2];
+        if (own[k] && i < X) {
+          const size_t xy = (size_t)Pn * g.Y + yk[k];
+          an[k][0] = __ldg(p.A + xy); an[k][1] = __ldg(p.A + XY + xy); an[k][2] = __ldg(p.A + 2 * XY + xy);
         }
+      }
+      const float4* const eC = sE + se * eslot;    // E^n[P]
+      const float4* const eN = sE + sen * eslot;   // E^n[P+1]
+      const float4* const hO = sH + sh * eslot;    // H^{n-1/2}[P]
+      const float4* const bC = sB + sh * eslot;    // B[P]
+      const float4* const pS = sP + sh * pslot + (2 * cp * g.npg + (has_psi ? slot : 0)) * PV;
+      const int pstep = g.npg * PV;                // item 1's psi vectors follow item 0's column
+
+      float ex[2][VW], ey[2][VW], ez[2][VW], hx[2][VW], hy[2][VW], hz[2][VW];
+      {
         float ah[VW], bh[VW], ikh[VW];
         load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
-        float ex_top = __shfl_down_sync(0xffffffffu, ex[0], 1);
-        float ey_top = __shfl_down_sync(0xffffffffu, ey[0], 1);
-        if (fix_up) {
-          float tmp[VW];
-          unpack(eC[tid + 1], tmp, T()); ex_top = tmp[0];
-          unpack(eC[NTc + tid + 1], tmp, T()); ey_top = tmp[0];
-        }
-        if (top) { ex_top = 0.f; ey_top = 0.f; }
 #pragma unroll
-        for (int v = 0; v < VW; ++v) {
-          const float exz = (v + 1 < VW) ? ex[(v + 1) % VW] : ex_top;
-          const float eyz = (v + 1 < VW) ? ey[(v + 1) % VW] : ey_top;
-          h_cell(ex[v], ey[v], ez[v], exz, eyz, ez_yp[v], ex_yp[v], ey_xp[v], ez_xp[v], ah[v], bh[v],
-                 ikh[v], g.dt, psx[v], psy[v], hx[v], hy[v], hz[v]);
-          hx[v] = round_store<T>(hx[v]); hy[v] = round_store<T>(hy[v]); hz[v] = round_store<T>(hz[v]);
+        for (int k = 0; k < 2; ++k) {
+          unpack(eC[f[k]], ex[k], T()); unpack(eC[ring + f[k]], ey[k], T());
+          unpack(eC[2 * ring + f[k]], ez[k], T());
+          unpack(hO[f[k]], hx[k], T()); unpack(hO[ring + f[k]], hy[k], T());
+          unpack(hO[2 * ring + f[k]], hz[k], T());
         }
-        if (psiH_thr && own && real) {             // new psiH of the owned PML cells
-          const size_t po = (size_t)P * pplane + poff;
-          float* const w0p = p.psiHs[wb][0] + po;
-          float* const w1p = p.psiHs[wb][1] + po;
 #pragma unroll
-          for (int v = 0; v < VW; v += 4) {
-            __stcg(reinterpret_cast<float4*>(w0p + v), make_float4(psx[v], psx[v + 1], psx[v + 2], psx[v + 3]));
-            __stcg(reinterpret_cast<float4*>(w1p + v), make_float4(psy[v], psy[v + 1], psy[v + 2], psy[v + 3]));
+        for (int k = 0; k < 2; ++k) {
+          float ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW], psx[VW], psy[VW];
+          if (k == 0) {
+#pragma unroll
+            for (int v = 0; v < VW; ++v) { ez_yp[v] = ez[1][v]; ex_yp[v] = ex[1][v]; }
+          } else {
+            const int nb = doH[1] ? f[1] + Zq : f[1];
+            unpack(eC[2 * ring + nb], ez_yp, T()); unpack(eC[nb], ex_yp, T());
+          }
+          unpack(eN[ring + f[k]], ey_xp, T()); unpack(eN[2 * ring + f[k]], ez_xp, T());
+#pragma unroll
+          for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
+          if (has_psi && doH[k]) { load_psi(pS + k * pstep, psx); load_psi(pS + k * pstep + npsi, psy); }
+          float ex_top = __shfl_down_sync(0xffffffffu, ex[k][0], 1);
+          float ey_top = __shfl_down_sync(0xffffffffu, ey[k][0], 1);
+          if (fix_up) {
+            float tmp[VW];
+            unpack(eC[f[k] + 1], tmp, T()); ex_top = tmp[0];
+            unpack(eC[ring + f[k] + 1], tmp, T()); ey_top = tmp[0];
+          }
+          if (top) { ex_top = 0.f; ey_top = 0.f; }
+#pragma unroll
+          for (int v = 0; v < VW; ++v) {
+            const float exz = (v + 1 < VW) ? ex[k][(v + 1) % VW] : ex_top;
+            const float eyz = (v + 1 < VW) ? ey[k][(v + 1) % VW] : ey_top;
+            h_cell(ex[k][v], ey[k][v], ez[k][v], exz, eyz, ez_yp[v], ex_yp[v], ey_xp[v], ez_xp[v],
+                   ah[v], bh[v], ikh[v], g.dt, psx[v], psy[v], hx[k][v], hy[k][v], hz[k][v]);
+            hx[k][v] = round_store<T>(hx[k][v]); hy[k][v] = round_store<T>(hy[k][v]);
+            hz[k][v] = round_store<T>(hz[k][v]);
+          }
+          if (has_psi && own[k] && real) {         // new psiH of the owned PML cells
+            const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
+            store_psi(p.psiHs[wb][0] + po, psx);
+            store_psi(p.psiHs[wb][1] + po, psy);
           }
         }
       }
 
-      const float4 hxv = pack(hx, T()), hyv = pack(hy, T()), hzv = pack(hz, T());
-      sX[tid] = hzv;
-      sX[NTc + tid] = hxv;
-      if (cfg.need_zfix) sX[2 * NTc + tid] = hyv;
+      // pair boundary: the odd column's new H is the y-1 neighbour of the next thread's even one
+      const float4 hx1v = pack(hx[1], T()), hz1v = pack(hz[1], T());
+      sX[tid] = hz1v;
+      sX[NTc + tid] = hx1v;
+      if (cfg.need_zfix) {                         // cross-warp z-1 neighbours need Hx, Hy of both
+        sX[2 * NTc + tid] = pack(hy[1], T());
+        sX[3 * NTc + tid] = pack(hx[0], T());
+        sX[4 * NTc + tid] = pack(hy[0], T());
+      }
       ok = bar_compute_and(NTc, ok);               // B_i (+ uniform failure decision)
       if (!ok) break;
       if (real) {
-        float hx_bot = __shfl_up_sync(0xffffffffu, hx[VW - 1], 1);
-        float hy_bot = __shfl_up_sync(0xffffffffu, hy[VW - 1], 1);
-        if (fix_dn) {
-          float tmp[VW];
-          unpack(sX[NTc + tid - 1], tmp, T()); hx_bot = tmp[VW - 1];
-          unpack(sX[2 * NTc + tid - 1], tmp, T()); hy_bot = tmp[VW - 1];
-        }
-        if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
-        if (own) {
-          const size_t offP = (size_t)P * gP + coff;
-          float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
-          unpack(sX[nbm], hz_ym, T());
-          unpack(sX[NTc + nbm], hx_ym, T());
+        float ae[VW], be[VW], ike[VW];
+        load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
+        const size_t pP = (size_t)P * gP;
 #pragma unroll
-          for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
-          if (psiE_thr) {
+        for (int k = 0; k < 2; ++k) {
+          float hx_bot = __shfl_up_sync(0xffffffffu, hx[k][VW - 1], 1);
+          float hy_bot = __shfl_up_sync(0xffffffffu, hy[k][VW - 1], 1);
+          if (fix_dn) {
+            float tmp[VW];
+            unpack(sX[(k == 1 ? NTc : 3 * NTc) + tid - 1], tmp, T()); hx_bot = tmp[VW - 1];
+            unpack(sX[(k == 1 ? 2 * NTc : 4 * NTc) + tid - 1], tmp, T()); hy_bot = tmp[VW - 1];
+          }
+          if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
+          if (own[k]) {
+            const size_t offP = pP + coff[k];
+            float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
+            if (k == 1) {
 #pragma unroll
-            for (int v = 0; v < PV; ++v) {
-              float4 r = pS[2 * npsi + v];
-              qsx[4 * v] = r.x; qsx[4 * v + 1] = r.y; qsx[4 * v + 2] = r.z; qsx[4 * v + 3] = r.w;
-              r = pS[3 * npsi + v];
-              qsy[4 * v] = r.x; qsy[4 * v + 1] = r.y; qsy[4 * v + 2] = r.z; qsy[4 * v + 3] = r.w;
+              for (int v = 0; v < VW; ++v) { hz_ym[v] = hz[0][v]; hx_ym[v] = hx[0][v]; }
+            } else {                               // even column >= 2: previous thread's odd column
+              unpack(sX[tid - Zq], hz_ym, T());
+              unpack(sX[NTc + tid - Zq], hx_ym, T());
             }
-          }
-          unpack(bC[tid], b0, T()); unpack(bC[NTc + tid], b1, T()); unpack(bC[2 * NTc + tid], b2, T());
-          float ae[VW], be[VW], ike[VW];
-          load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
 #pragma unroll
-          for (int v = 0; v < VW; ++v) {
-            const float hxz = (v > 0) ? hx[(v + VW - 1) % VW] : hx_bot;
-            const float hyz = (v > 0) ? hy[(v + VW - 1) % VW] : hy_bot;
-            e_cell(hx[v], hy[v], hz[v], hxz, hyz, hz_ym[v], hx_ym[v], hyp[v], hzp[v], ae[v], be[v],
-                   ike[v], a0, a1, a2, b0[v], b1[v], b2[v], qsx[v], qsy[v], ex[v], ey[v], ez[v]);
-          }
-          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : src_thr)
-            add_source<VW>(g, p.src, w0, w1, P, y, q, ex, ey, ez);
-          st16<LD_CG>(p.Hs[wb][0] + offP, hxv);
-          st16<LD_CG>(p.Hs[wb][1] + offP, hyv);
-          st16<LD_CG>(p.Hs[wb][2] + offP, hzv);
-          store_vec<T, LD_CG>(p.Es[wb][0] + offP, ex);
-          store_vec<T, LD_CG>(p.Es[wb][1] + offP, ey);
-          store_vec<T, LD_CG>(p.Es[wb][2] + offP, ez);
-          if (psiE_thr) {
-            const size_t po = (size_t)P * pplane + poff;
-#pragma unroll
-            for (int v = 0; v < VW; v += 4) {
-              __stcg(reinterpret_cast<float4*>(p.psiE[0] + po + v),
-                     make_float4(qsx[v], qsx[v + 1], qsx[v + 2], qsx[v + 3]));
-              __stcg(reinterpret_cast<float4*>(p.psiE[1] + po + v),
-                     make_float4(qsy[v], qsy[v + 1], qsy[v + 2], qsy[v + 3]));
-            }
-          }
-          if (oi >= 0) {
+            for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
+            if (has_psi) { load_psi(pS + k * pstep + 2 * npsi, qsx); load_psi(pS + k * pstep + 3 * npsi, qsy); }
+            unpack(bC[f[k]], b0, T()); unpack(bC[ring + f[k]], b1, T()); unpack(bC[2 * ring + f[k]], b2, T());
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
-              ex[v] = round_store<T>(ex[v]); ey[v] = round_store<T>(ey[v]);
-              ez[v] = round_store<T>(ez[v]);
+              const float hxz = (v > 0) ? hx[k][(v + VW - 1) % VW] : hx_bot;
+              const float hyz = (v > 0) ? hy[k][(v + VW - 1) % VW] : hy_bot;
+              e_cell(hx[k][v], hy[k][v], hz[k][v], hxz, hyz, hz_ym[v], hx_ym[v], hyp[k][v], hzp[k][v],
+                     ae[v], be[v], ike[v], a[k][0], a[k][1], a[k][2], b0[v], b1[v], b2[v], qsx[v],
+                     qsy[v], ex[k][v], ey[k][v], ez[k][v]);
             }
-            write_snapshot<VW>(g, p.out, oi, P, y, q, ex, ey, ez);
+            if (g.src_axis == 0 ? (P == sp0 || P == sp1) : src_thr[k])
+              add_source<VW>(g, p.src, w0, w1, P, yk[k], q, ex[k], ey[k], ez[k]);
+            store_vec<T, LD_CG>(p.Hs[wb][0] + offP, hx[k]);
+            store_vec<T, LD_CG>(p.Hs[wb][1] + offP, hy[k]);
+            store_vec<T, LD_CG>(p.Hs[wb][2] + offP, hz[k]);
+            store_vec<T, LD_CG>(p.Es[wb][0] + offP, ex[k]);
+            store_vec<T, LD_CG>(p.Es[wb][1] + offP, ey[k]);
+            store_vec<T, LD_CG>(p.Es[wb][2] + offP, ez[k]);
+            if (has_psi) {
+              const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
+              store_psi(p.psiE[0] + po, qsx);
+              store_psi(p.psiE[1] + po, qsy);
+            }
+            if (oi >= 0) {
+#pragma unroll
+              for (int v = 0; v < VW; ++v) {
+                ex[k][v] = round_store<T>(ex[k][v]); ey[k][v] = round_store<T>(ey[k][v]);
+                ez[k][v] = round_store<T>(ez[k][v]);
+              }
+              write_snapshot<VW>(g, p.out, oi, P, yk[k], q, ex[k], ey[k], ez[k]);
+            }
           }
         }
       }
 #pragma unroll
-      for (int v = 0; v < VW; ++v) { hyp[v] = hy[v]; hzp[v] = hz[v]; }
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int v = 0; v < VW; ++v) { hyp[k][v] = hy[k][v]; hzp[k][v] = hz[k][v]; }
       P = Pn;
       se = sen;
       sh = sh + 1 == NH ? 0 : sh + 1;
@@ -505,11 +546,19 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   if (tid == 0) st_vol_s(&ctl.exit_, 1u);
 }
 
+// compute threads of a CTA that owns `tile_y` columns: one thread per z-vector of a column pair
+inline int systolic2_compute_threads(const Geom& g, int tile_y) {
+  return ((tile_y + 3) / 2 * g.Zq + 31) / 32 * 32;
+}
+
 template <typename T, int D>
-size_t systolic2_smem_bytes(const Geom& g, int compute_threads, int tile_y) {
+size_t systolic2_smem_bytes(const Geom& g, int tile_y) {
   constexpr int PV = VecTraits<T>::VW / 4;
   const size_t npsi = (size_t)(tile_y + 2) * g.npg * PV;
-  return sizeof(float4) * ((size_t)((D + 2) * 3 + 2 * (D + 1) * 3 + 3) * compute_threads +
+  const size_t ring = (size_t)(tile_y + 2) * g.Zq;
+  const bool zfix = 32 % g.Zq != 0;
+  return sizeof(float4) * ((size_t)((D + 2) * 3 + 2 * (D + 1) * 3) * ring +
+                           (size_t)(zfix ? 5 : 2) * systolic2_compute_threads(g, tile_y) +
                            (size_t)(D + 1) * 4 * npsi + 6 * (size_t)g.Zp / 4);
 }
 
@@ -518,24 +567,23 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
                            int l2_bytes, SystolicCfg* cfg, std::string* why) {
   const int max_threads = threads_req > 0 ? (threads_req < kSys2MaxCompute ? threads_req : kSys2MaxCompute)
                                           : kSys2MaxCompute;
-  if (g.Zq * 3 > max_threads) { *why = "z extent too large for one CTA"; return false; }
-  int max_tile = max_threads / g.Zq - 2;
+  if (g.Zq * 2 > max_threads) { *why = "z extent too large for one CTA"; return false; }
+  int max_tile = 2 * (max_threads / g.Zq) - 2;
   // largest tile whose staging ring fits in shared memory
-  while (max_tile >= 1 &&
-         systolic2_smem_bytes<T, D>(g, ((max_tile + 2) * g.Zq + 31) / 32 * 32, max_tile) + 64 >
-             227 * 1024)
+  while (max_tile >= 1 && (systolic2_compute_threads(g, max_tile) > max_threads ||
+                           systolic2_smem_bytes<T, D>(g, max_tile) + 64 > 227 * 1024))
     --max_tile;
   if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
   if (max_tile > g.Y) max_tile = g.Y;
   const int ntiles = (g.Y + max_tile - 1) / max_tile;
   const int widest = (g.Y + ntiles - 1) / ntiles;
-  const int compute = ((widest + 2) * g.Zq + 31) / 32 * 32;
+  const int compute = systolic2_compute_threads(g, widest);
   cfg->tile_y = widest;
   cfg->ntiles = ntiles;
   cfg->threads = compute + kSys2Service;
   cfg->need_zfix = (32 % g.Zq != 0);
-  cfg->smem_bytes = (int)systolic2_smem_bytes<T, D>(g, compute, widest);
+  cfg->smem_bytes = (int)systolic2_smem_bytes<T, D>(g, widest);
   // >= 2D+4 is needed for deadlock freedom (a throttled stage has published i-2 indices while its
   // successor needs i'+D+2 of them to advance); the rest is slack for the
   // polling/publishing latency.

@@ -13,9 +13,11 @@ ENVV=""
 run --kernel systolic_async --prefetch 1
 run --kernel systolic_async --prefetch 2
 run --kernel systolic_async --prefetch 1 --stages 1
+run --kernel systolic_async --prefetch 1 --stages 4
 run --kernel systolic_async --prefetch 1 --tile-y 8
-run --kernel systolic_async --prefetch 2 --tile-y 6
+run --kernel systolic_async --prefetch 1 --tile-y 6
 ENVV="B200FDTD_PF_AHEAD=0"; run --kernel systolic_async --prefetch 1
-} | tee gpurun_out/sweep_v4.log
+ENVV="B200FDTD_MAX_LEAD=6"; run --kernel systolic_async --prefetch 1
+} | tee gpurun_out/sweep_v5.log
 echo "== ncu full async"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:systolic2_kernel -c 1 -o gpurun_out/prof_async -f $B --tt 200 --steps 1 --warmup 0 --kernel systolic_async --prefetch 1 > gpurun_out/ncu_full_async.log 2>&1; tail -2 gpurun_out/ncu_full_async.log
