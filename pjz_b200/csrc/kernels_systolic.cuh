@@ -45,6 +45,7 @@ struct SystolicCfg {
   int need_zfix;         // z-columns straddle warps (Zq does not divide 32)
   int trap_on_timeout;
   int pf_ahead;          // systolic_async: planes of L2 prefetch beyond the staging ring
+  int svc_sleep_ns;      // systolic_async: back-off of the poller / publisher warps
   long long l2_window_bytes;
 };
 

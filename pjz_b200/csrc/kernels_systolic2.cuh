@@ -181,7 +181,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         }
       }
       pf_done = __shfl_sync(0xffffffffu, pf_done, 8);
-      __nanosleep(200);
+      __nanosleep(cfg.svc_sleep_ns);
     }
     return;
   }
@@ -198,7 +198,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         } else if (ex) {
           break;
         } else {
-          __nanosleep(200);
+          __nanosleep(cfg.svc_sleep_ns);
         }
       }
     }
@@ -229,8 +229,17 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   }
   const int slot = psi_slot(g, q);
   const bool has_psi = slot >= 0;
-  const size_t pplane = (size_t)g.Y * g.npg * VW;
-  const size_t gP = (size_t)g.P;
+  size_t pplane = (size_t)g.Y * g.npg * VW;
+  size_t gP = (size_t)g.P;
+  size_t ppoff[2];                                 // psi offset of the item inside a plane
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    ppoff[k] = ((size_t)yk[k] * g.npg + (has_psi ? slot : 0)) * VW;
+    // Loop invariants are laundered through an empty asm: otherwise ptxas rematerialises these
+    // 64-bit multiply chains inside the sweep loop (measured: ~170 instructions per iteration).
+    asm volatile("" : "+l"(coff[k]), "+l"(ppoff[k]), "+r"(f[k]));
+  }
+  asm volatile("" : "+l"(pplane), "+l"(gP));
   const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < Zq;
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
   const bool top = q + 1 == Zq, bottom = q == 0;
@@ -333,7 +342,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
           }
           if (has_psi) {
             float4* ps = sP + sh * pslot + ((2 * cp + k) * g.npg + slot) * PV;
-            const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
+            const size_t po = (size_t)P * pplane + ppoff[k];
 #pragma unroll
             for (int v = 0; v < PV; ++v) {
               cp_async16(ps + v, p.psiHs[rb][0] + po + 4 * v);
@@ -354,13 +363,13 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     int PL = wrapi(cstart - 1, X);                 // plane whose H/B/psi the next issue() loads
 #pragma unroll
     for (int it = 0; it < D; ++it) {
-      ok = ok && wait_deps(it);
+      if (tid == 0) ok = ok && wait_deps(it);
+      ok = bar_compute_and(NTc, ok);
       const int PLn = PL + 1 == X ? 0 : PL + 1;
       if (ok && it <= X) issue(PL, PLn, it + 1, it, it == 0, it >= 1);
       cp_async_commit();
       PL = PLn;
     }
-    ok = bar_compute_and(NTc, ok);
 
     float hyp[2][VW], hzp[2][VW];                  // H^{n+1/2}[P-1] of the thread's own cells
 #pragma unroll
@@ -375,14 +384,18 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       const bool real = i >= 1;
       const int Pn = P + 1 == X ? 0 : P + 1;
       const int sen = se + 1 == NE ? 0 : se + 1;   // slot of E[P+1]
+      const size_t pP = (size_t)P * gP, psiP = (size_t)P * pplane;
       cp_async_wait<D - 1>();
-      bar_compute(NTc);                            // A_i
+      // One thread checks the dependencies of the loads issued below; barrier A_i carries the
+      // verdict to everybody (and makes the landed ring slot visible).
+      if (tid == 0) ok = wait_deps(i + D);
+      ok = bar_compute_and(NTc, ok);               // A_i
+      if (!ok) break;
       if (tid == 0) {
         // every store of iterations < i has been issued by all compute threads
         if (i >= 2) st_vol_s(&ctl.done, base_mine + (unsigned)(i - 1));
         st_vol_s(&ctl.front, iters_done + (unsigned)i);
       }
-      ok = wait_deps(i + D);
       {
         const int PLn = PL + 1 == X ? 0 : PL + 1;
         // loads of iteration i+D go to the slots freed by iteration i-1
@@ -451,7 +464,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             hz[k][v] = round_store<T>(hz[k][v]);
           }
           if (has_psi && own[k] && real) {         // new psiH of the owned PML cells
-            const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
+            const size_t po = psiP + ppoff[k];
             store_psi(p.psiHs[wb][0] + po, psx);
             store_psi(p.psiHs[wb][1] + po, psy);
           }
@@ -467,12 +480,10 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         sX[3 * NTc + tid] = pack(hx[0], T());
         sX[4 * NTc + tid] = pack(hy[0], T());
       }
-      ok = bar_compute_and(NTc, ok);               // B_i (+ uniform failure decision)
-      if (!ok) break;
+      bar_compute(NTc);                            // B_i
       if (real) {
         float ae[VW], be[VW], ike[VW];
         load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
-        const size_t pP = (size_t)P * gP;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           float hx_bot = __shfl_up_sync(0xffffffffu, hx[k][VW - 1], 1);
@@ -514,7 +525,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             store_vec<T, LD_CG>(p.Es[wb][1] + offP, ey[k]);
             store_vec<T, LD_CG>(p.Es[wb][2] + offP, ez[k]);
             if (has_psi) {
-              const size_t po = (size_t)P * pplane + ((size_t)yk[k] * g.npg + slot) * VW;
+              const size_t po = psiP + ppoff[k];
               store_psi(p.psiE[0] + po, qsx);
               store_psi(p.psiE[1] + po, qsy);
             }
@@ -589,9 +600,11 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   // polling/publishing latency.
   cfg->max_lead = 2 * D + 8;
   cfg->pf_ahead = 6;
+  cfg->svc_sleep_ns = 400;
   // tuning knobs (benchmark sweeps only; values below the deadlock bound are clamped)
   if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
   if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
+  if (const char* e = getenv("B200FDTD_SVC_SLEEP")) cfg->svc_sleep_ns = atoi(e);
   if (cfg->max_lead < 2 * D + 4) cfg->max_lead = 2 * D + 4;
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
