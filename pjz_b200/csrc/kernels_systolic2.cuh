@@ -41,8 +41,11 @@
 
 namespace b200 {
 
-constexpr int kSys2MaxCompute = 256;   // 8 warps, two columns per thread
-constexpr int kSys2Service = 64;       // poller warp + publisher warp
+// Registers are partitioned per SM sub-partition (16 Ki each): with 8 warps per CTA every
+// sub-partition holds 2 warps and a thread may use up to 255 registers; a 9th/10th warp would
+// cap it at 168 and spill (measured: local-memory traffic halves the throughput).
+constexpr int kSys2MaxCompute = 224;   // 7 warps, two columns per thread
+constexpr int kSys2Service = 32;       // one service warp: poller + publisher + L2 prefetcher
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -149,7 +152,17 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     const size_t pf_off = (size_t)ylo * g.Zp;
     unsigned pf_done = 0;                          // cumulative iterations already prefetched
     const unsigned sweep_iters = (unsigned)g.X + 1u;
-    while (ld_vol_s(&ctl.exit_) == 0) {
+    unsigned published = 0;
+    while (true) {
+      // publisher duty (lane 0): st.release.gpu = fence + store, whenever `done` advanced
+      const unsigned ex = ld_vol_s(&ctl.exit_);
+      const unsigned dn = ld_vol_s(&ctl.done);
+      if (dn != published) {
+        if (lane == 0) st_release_u32(my_prog, dn);
+        published = dn;
+      } else if (ex) {
+        break;
+      }
       unsigned v = 0xffffffffu;
       if (lane < 5) v = ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
@@ -185,25 +198,6 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     }
     return;
   }
-  // ================================== publisher warp =============================================
-  if (tid >= NTc + 32) {
-    if (lane == 0) {
-      unsigned last = 0;
-      while (true) {
-        const unsigned ex = ld_vol_s(&ctl.exit_);
-        const unsigned d = ld_vol_s(&ctl.done);
-        if (d != last) {
-          st_release_u32(my_prog, d);              // fence.acq_rel.gpu + store
-          last = d;
-        } else if (ex) {
-          break;
-        } else {
-          __nanosleep(cfg.svc_sleep_ns);
-        }
-      }
-    }
-    return;
-  }
 
   // ================================= compute warps ===============================================
   // One thread owns the 16-byte z-vector q of TWO adjacent columns (2cp, 2cp+1) of the loaded
@@ -216,7 +210,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const int ncols = Yt + 2;
   int f[2], yk[2];
   bool act[2], doH[2], own[2];
-  size_t coff[2];
+  unsigned coff[2];                                // element offset inside a plane (< 2^31)
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int c = 2 * cp + k;
@@ -225,21 +219,16 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     own[k] = c >= 1 && c <= Yt;
     yk[k] = wrapi(y0 - 1 + (act[k] ? c : 0), g.Y);
     f[k] = act[k] ? c * Zq + q : q;                // ring index of the item (in range if idle)
-    coff[k] = ((size_t)yk[k] * Zq + q) * VW;
+    coff[k] = (unsigned)((yk[k] * Zq + q) * VW);
   }
   const int slot = psi_slot(g, q);
   const bool has_psi = slot >= 0;
-  size_t pplane = (size_t)g.Y * g.npg * VW;
-  size_t gP = (size_t)g.P;
-  size_t ppoff[2];                                 // psi offset of the item inside a plane
+  const size_t pplane = (size_t)g.Y * g.npg * VW;
+  const size_t gP = (size_t)g.P;
+  unsigned ppoff[2];                               // psi offset of the item inside a plane (< 2^31)
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    ppoff[k] = ((size_t)yk[k] * g.npg + (has_psi ? slot : 0)) * VW;
-    // Loop invariants are laundered through an empty asm: otherwise ptxas rematerialises these
-    // 64-bit multiply chains inside the sweep loop (measured: ~170 instructions per iteration).
-    asm volatile("" : "+l"(coff[k]), "+l"(ppoff[k]), "+r"(f[k]));
-  }
-  asm volatile("" : "+l"(pplane), "+l"(gP));
+  for (int k = 0; k < 2; ++k)
+    ppoff[k] = (unsigned)((yk[k] * g.npg + (has_psi ? slot : 0)) * VW);
   const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < Zq;
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
   const bool top = q + 1 == Zq, bottom = q == 0;
@@ -321,7 +310,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       float4* const bb = sB + sh * eslot;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        if (!act[k]) continue;
+        if (act[k]) {
         const size_t offP = pP + coff[k], offN = pN + coff[k];
         cp_async16(eb + f[k], p.Es[rb][0] + offN);
         cp_async16(eb + 2 * ring + f[k], p.Es[rb][2] + offN);
@@ -353,6 +342,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
               }
             }
           }
+        }
         }
       }
     };
