@@ -180,54 +180,46 @@ template <int VW>
 __device__ __forceinline__ void add_source(const Geom& g, const float* __restrict__ src,
                                            float w0, float w1, int x, int y, int q,
                                            float (&ex)[VW], float (&ey)[VW], float (&ez)[VW]) {
-  if (g.src_axis == 0) {
+  // Written with selects instead of conditional element updates: a conditionally updated
+  // register array makes ptxas demote the whole array to local memory (measured: 64 B of
+  // local traffic per thread per plane in the systolic kernel).
+  if (g.src_axis == 0 || g.src_axis == 1) {
+    const bool ax0 = g.src_axis == 0;
+    const int n = ax0 ? g.X : g.Y, pos = ax0 ? x : y, line = ax0 ? y : x;
+    const float* s0 = src + (size_t)line * g.Z;
+    const float* s1 = s0 + (size_t)(ax0 ? g.Y : g.X) * g.Z;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-      if (x == wrapi(g.src_pos - ch, g.X)) {
-        const float w = ch ? w1 : w0;
-        const float* s0 = src + (size_t)y * g.Z;
-        const float* s1 = src + (size_t)g.Y * g.Z + (size_t)y * g.Z;
+      const bool plane_hit = pos == wrapi(g.src_pos - ch, n);
+      const float w = ch ? w1 : w0;
 #pragma unroll
-        for (int i = 0; i < VW; ++i) {
-          const int z = q * VW + i;
-          if (z < g.Z) {
-            ey[i] = fmaf(w, __ldg(s0 + z), ey[i]);
-            ez[i] = fmaf(w, __ldg(s1 + z), ez[i]);
-          }
-        }
+      for (int i = 0; i < VW; ++i) {
+        const int z = q * VW + i;
+        const bool hit = plane_hit && z < g.Z;
+        const float a = hit ? __ldg(s0 + z) : 0.f, b = hit ? __ldg(s1 + z) : 0.f;
+        const float t0 = fmaf(w, a, ax0 ? ey[i] : ex[i]);
+        const float t2 = fmaf(w, b, ez[i]);
+        ey[i] = (hit && ax0) ? t0 : ey[i];
+        ex[i] = (hit && !ax0) ? t0 : ex[i];
+        ez[i] = hit ? t2 : ez[i];
       }
     }
-  } else if (g.src_axis == 1) {
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      if (y == wrapi(g.src_pos - ch, g.Y)) {
-        const float w = ch ? w1 : w0;
-        const float* s0 = src + (size_t)x * g.Z;
-        const float* s1 = src + (size_t)g.X * g.Z + (size_t)x * g.Z;
-#pragma unroll
-        for (int i = 0; i < VW; ++i) {
-          const int z = q * VW + i;
-          if (z < g.Z) {
-            ex[i] = fmaf(w, __ldg(s0 + z), ex[i]);
-            ez[i] = fmaf(w, __ldg(s1 + z), ez[i]);
-          }
-        }
-      }
-    }
-  } else if (q == g.src_pos / VW) {
+  } else {
+    const bool qhit = q == g.src_pos / VW;
+    const int idx = g.src_pos % VW;
     const size_t XY = (size_t)g.X * g.Y, xy = (size_t)x * g.Y + y;
     const float s00 = __ldg(src + xy), s01 = __ldg(src + XY + xy);
     const float s10 = __ldg(src + 2 * XY + xy), s11 = __ldg(src + 3 * XY + xy);
 #pragma unroll
     for (int i = 0; i < VW; ++i) {
-      if (i == g.src_pos % VW) {
-        float e0 = ex[i], e1 = ey[i];
-        e0 = fmaf(w0, s00, e0);
-        e1 = fmaf(w0, s01, e1);
-        e0 = fmaf(w1, s10, e0);
-        e1 = fmaf(w1, s11, e1);
-        ex[i] = e0; ey[i] = e1;
-      }
+      const bool hit = qhit && i == idx;
+      float e0 = ex[i], e1 = ey[i];
+      e0 = fmaf(w0, s00, e0);
+      e1 = fmaf(w0, s01, e1);
+      e0 = fmaf(w1, s10, e0);
+      e1 = fmaf(w1, s11, e1);
+      ex[i] = hit ? e0 : ex[i];
+      ey[i] = hit ? e1 : ey[i];
     }
   }
 }
