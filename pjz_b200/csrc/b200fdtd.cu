@@ -131,8 +131,8 @@ static bool configure_async(const Geom& g, const b200fdtd_desc* d, int depth, in
   return false;
 }
 
-// AUTO: cp.async-staged systolic kernel with the deepest ring that fits (2 preferred), else the
-// register-staged one, else the per-step kernels.
+// AUTO: cp.async-staged systolic kernel (prefetch distance 1 measured fastest: a deeper ring
+// only shrinks the tile), else the register-staged one, else the per-step kernels.
 template <typename T>
 static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   plan->kernel = d->kernel;
@@ -143,15 +143,11 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   if (rc) return rc;
   std::string why;
   if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {
-    const int order[3] = {2, 1, 3};
-    for (int i = 0; i < 3; ++i) {
-      const int depth = d->prefetch > 0 ? d->prefetch : order[i];
-      if (configure_async<T>(g, d, depth, sms, l2, &plan->sys, &why)) {
-        plan->kernel = B200FDTD_KERNEL_SYSTOLIC_ASYNC;
-        plan->depth = depth;
-        return B200FDTD_OK;
-      }
-      if (d->prefetch > 0 || i == 1) break;
+    const int depth = d->prefetch > 0 ? d->prefetch : 1;
+    if (configure_async<T>(g, d, depth, sms, l2, &plan->sys, &why)) {
+      plan->kernel = B200FDTD_KERNEL_SYSTOLIC_ASYNC;
+      plan->depth = depth;
+      return B200FDTD_OK;
     }
     if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC)
       return fail(B200FDTD_EUNSUPPORTED, "systolic_async kernel unavailable: %s", why.c_str());

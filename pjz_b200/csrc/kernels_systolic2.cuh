@@ -47,12 +47,15 @@ namespace b200 {
 constexpr int kSys2MaxCompute = 224;   // 7 warps, two columns per thread
 constexpr int kSys2Service = 32;       // one service warp: poller + publisher + L2 prefetcher
 
+// No "memory" clobber on the copy/commit: the slot being filled is not read before the
+// wait_group + barrier of a LATER iteration (both are compiler barriers), and without the clobber
+// ptxas is free to interleave this iteration's shared-memory reads with the copy issue.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.commit_group;");
 }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
