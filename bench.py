@@ -310,10 +310,17 @@ def main():
   else:
     dominant = "twopass_h_kernel + twopass_e_kernel (2 launches per FDTD step)"
     launches = (3 + 2 * tt) * args.steps
+  per_launch_updates = cells * (tt if info["kernel"].startswith("systolic") else 0.5)
+  # ncu DRAM bytes are only quoted for the configuration they were captured on
+  have_traffic = (traffic is not None and info["kernel"] == "systolic_async" and
+                  args.workload == "bend" and not args.reduced)
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-              "frac": achieved / peak, "traffic": traffic["bytes_per_launch"] if traffic else None,
+              "frac": achieved / peak,
+              "traffic": traffic["dram_bytes_per_cell_update"] * per_launch_updates
+              if have_traffic else None,
+              "traffic_source": traffic["from"] if have_traffic else None,
               "kernel": dominant, "peak_source": peak_src,
-              "algorithmic_bytes_per_launch": bpc * cells * (tt if info["kernel"].startswith("systolic") else 0.5),
+              "algorithmic_bytes_per_launch": bpc * per_launch_updates,
               "bytes_per_cell_update": bpc}
 
   cpu = None
