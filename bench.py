@@ -158,6 +158,14 @@ def ncu_traffic():
     return None
 
 
+def host_threads():
+  """All host threads the process may use (torchrun pins OMP_NUM_THREADS=1; ignore that)."""
+  try:
+    return max(1, len(os.sched_getaffinity(0)))
+  except AttributeError:
+    return os.cpu_count() or 1
+
+
 def cpu_sample(host, dims, seconds, reduced):
   """Oracle port (C, OpenMP, all host threads) on a bounded sample of the SAME workload:
   the same domain and inputs, the first n time steps; set-up time removed by differencing."""
@@ -165,12 +173,14 @@ def cpu_sample(host, dims, seconds, reduced):
   cells = dims[0] * dims[1] * dims[2]
   kw = dict(host)
   kw["launch_params"] = None
+  nthr = host_threads()
 
   def timed(n):
     t0 = time.perf_counter()
-    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False)
+    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False, nthreads=nthr)
     return time.perf_counter() - t0
 
+  timed(0)
   t_setup = timed(0)
   n1 = 4
   t1 = timed(n1)
@@ -178,7 +188,7 @@ def cpu_sample(host, dims, seconds, reduced):
   n2 = int(max(8, min(host["source_waveform"].shape[0], seconds * rate / cells)))
   t2 = timed(n2)
   value = cells * n2 / max(t2 - t_setup, 1e-6) / 1e9
-  return {"value": value, "unit": UNIT, "cores": fdtd_c.max_threads(), "kind": "port",
+  return {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
           "sample": f"same workload, first {n2} of {host['source_waveform'].shape[0]} FDTD steps "
                     f"({t2 - t_setup:.1f} s of CPU work, set-up excluded), fp"
                     f"{'16-storage' if reduced else '32'} C oracle with OpenMP"}
@@ -194,26 +204,29 @@ def run_reference(args, rank, world):
   cells = dims[0] * dims[1] * dims[2]
   kw = dict(host)
   kw["launch_params"] = None
-  t0 = time.perf_counter()
-  fdtd_c.fdtdz(**kw, steps_override=0, want_output=False)
-  t_setup = time.perf_counter() - t0
-  n = 24
+  nthr = host_threads()
+
+  def timed(n):
+    t0 = time.perf_counter()
+    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False, nthreads=nthr)
+    return time.perf_counter() - t0
+
+  timed(0)
+  t_setup = min(timed(0), timed(0))
+  n = 100
   for _ in range(args.warmup):
-    fdtd_c.fdtdz(**kw, steps_override=4, want_output=False)
-  t0 = time.perf_counter()
-  for _ in range(args.steps):
-    fdtd_c.fdtdz(**kw, steps_override=n, want_output=False)
-  dt = time.perf_counter() - t0 - args.steps * t_setup
+    timed(4)
+  dt = sum(timed(n) for _ in range(args.steps)) - args.steps * t_setup
   value = cells * n * args.steps / max(dt, 1e-9) / 1e9
-  cores = fdtd_c.max_threads()
-  sample = f"each step = first {n} of {tt} FDTD steps of the same workload; set-up excluded"
+  sample = (f"each step = first {n} of {tt} FDTD steps of the same workload, all {nthr} host "
+            f"threads; set-up ({t_setup:.2f} s per call) excluded")
   print(json.dumps({
       "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f16-storage/f32-math" if args.reduced else "f32", "data": "synthetic",
       "config": {"workload": name, "grid": list(dims), "fdtd_steps": tt},
-      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
                        "sample": sample},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }))
