@@ -107,9 +107,7 @@ struct Sys2Ctl {
   unsigned exit_;     // compute warps are finished
 };
 
-// NC / ZQ: compile-time copies of (tile_y + 2) and Zq for the common geometries (0 = take the
-// run-time value).  With both known, every shared-memory offset below is an immediate.
-template <typename T, int D, int NC, int ZQ>
+template <typename T, int D>
 __global__ void __launch_bounds__(kSys2MaxCompute + kSys2Service)
 systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sync) {
   constexpr int VW = VecTraits<T>::VW;
@@ -117,17 +115,14 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   constexpr int PV = VW / 4;                     // float4 per psi vector
   extern __shared__ float4 smem[];
   __shared__ Sys2Ctl ctl;
-  const int Zq = ZQ ? ZQ : g.Zq;
-  const int ncols_cta = NC ? NC : cfg.tile_y + 2;
-  const int NTc = (NC && ZQ) ? ((NC + 1) / 2 * ZQ + 31) / 32 * 32
-                             : (int)blockDim.x - kSys2Service;   // compute threads
+  const int NTc = blockDim.x - kSys2Service;     // compute threads
   const int tid = threadIdx.x, lane = tid & 31;
   const int S = cfg.stages, NT = cfg.ntiles;
   const int t = blockIdx.x % NT, j = blockIdx.x / NT;
   const int y0 = (int)((long long)t * g.Y / NT);
   const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
-  const int npsi = ncols_cta * g.npg * PV;        // float4 per psi array per slot
-  const int ring = ncols_cta * Zq;                // float4 per component per ring slot
+  const int npsi = (cfg.tile_y + 2) * g.npg * PV; // float4 per psi array per slot
+  const int ring = (cfg.tile_y + 2) * g.Zq;       // float4 per component per ring slot
   const int eslot = 3 * ring, pslot = 4 * npsi;   // float4 per E/H/B slot, per psi slot
 
   float4* const sE = smem;                                   // [NE][3][ring]
@@ -213,29 +208,22 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   // neighbour of the odd column are the thread's own registers; only the pair boundary goes
   // through shared memory.  Everything that does not change along the sweep is computed here,
   // once: the loop body is issue-bound.
-  //
-  // To keep the loop straight-line, every loaded column is treated alike: all of its vectors
-  // are staged and both half-steps are formed for it (the halo columns' E and the last column's H
-  // are garbage that nobody reads); only the STORES are predicated on ownership.
-  const int X = g.X;
+  const int Zq = g.Zq, X = g.X;
   const int cp = tid / Zq, q = tid - cp * Zq;
   const int ncols = Yt + 2;
   int f[2], yk[2];
-  bool act[2], own[2];
+  bool act[2], doH[2], own[2];
   unsigned coff[2];                                // element offset inside a plane (< 2^31)
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int c = 2 * cp + k;
     act[k] = c < ncols;
+    doH[k] = c <= Yt;
     own[k] = c >= 1 && c <= Yt;
     yk[k] = wrapi(y0 - 1 + (act[k] ? c : 0), g.Y);
     f[k] = act[k] ? c * Zq + q : q;                // ring index of the item (in range if idle)
     coff[k] = (unsigned)((yk[k] * Zq + q) * VW);
   }
-  // y+1 neighbour of the odd column = even column of the next thread; the last loaded column
-  // has none (its H is never used): point it at itself.  y-1 of the even column likewise.
-  const int nb_up = (2 * cp + 2 < ncols) ? f[1] + Zq : f[1];
-  const int nb_dn = cp > 0 ? tid - Zq : tid;
   const int slot = psi_slot(g, q);
   const bool has_psi = slot >= 0;
   const size_t pplane = (size_t)g.Y * g.npg * VW;
@@ -318,7 +306,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     };
 
     // Async copies consumed by one iteration: E[Pn] -> E slot `se`, H/B/psi[P] -> slot `sh`.
-    auto issue = [&](int P, int Pn, int se, int sh, bool first) {
+    auto issue = [&](int P, int Pn, int se, int sh, bool first, bool ecoef) {
       const size_t pP = (size_t)P * gP, pN = (size_t)Pn * gP;
       float4* const eb = sE + se * eslot;
       float4* const hb = sH + sh * eslot;
@@ -326,21 +314,24 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         if (act[k]) {
-          const size_t offP = pP + coff[k], offN = pN + coff[k];
-          cp_async16(eb + f[k], p.Es[rb][0] + offN);
-          cp_async16(eb + ring + f[k], p.Es[rb][1] + offN);
-          cp_async16(eb + 2 * ring + f[k], p.Es[rb][2] + offN);
-          if (first) {                             // very first plane of the sweep: E[P] too
-            cp_async16(sE + f[k], p.Es[rb][0] + offP);
-            cp_async16(sE + ring + f[k], p.Es[rb][1] + offP);
-            cp_async16(sE + 2 * ring + f[k], p.Es[rb][2] + offP);
-          }
+        const size_t offP = pP + coff[k], offN = pN + coff[k];
+        cp_async16(eb + f[k], p.Es[rb][0] + offN);
+        cp_async16(eb + 2 * ring + f[k], p.Es[rb][2] + offN);
+        if (doH[k]) cp_async16(eb + ring + f[k], p.Es[rb][1] + offN);
+        if (first) {                               // very first plane of the sweep: E[P] too
+          cp_async16(sE + f[k], p.Es[rb][0] + offP);
+          cp_async16(sE + 2 * ring + f[k], p.Es[rb][2] + offP);
+          if (doH[k]) cp_async16(sE + ring + f[k], p.Es[rb][1] + offP);
+        }
+        if (doH[k]) {
           cp_async16(hb + f[k], p.Hs[rb][0] + offP);
           cp_async16(hb + ring + f[k], p.Hs[rb][1] + offP);
           cp_async16(hb + 2 * ring + f[k], p.Hs[rb][2] + offP);
-          cp_async16(bb + f[k], p.B[0] + offP);
-          cp_async16(bb + ring + f[k], p.B[1] + offP);
-          cp_async16(bb + 2 * ring + f[k], p.B[2] + offP);
+          if (own[k] && ecoef) {
+            cp_async16(bb + f[k], p.B[0] + offP);
+            cp_async16(bb + ring + f[k], p.B[1] + offP);
+            cp_async16(bb + 2 * ring + f[k], p.B[2] + offP);
+          }
           if (has_psi) {
             float4* ps = sP + sh * pslot + ((2 * cp + k) * g.npg + slot) * PV;
             const size_t po = (size_t)P * pplane + ppoff[k];
@@ -348,10 +339,13 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             for (int v = 0; v < PV; ++v) {
               cp_async16(ps + v, p.psiHs[rb][0] + po + 4 * v);
               cp_async16(ps + npsi + v, p.psiHs[rb][1] + po + 4 * v);
-              cp_async16(ps + 2 * npsi + v, p.psiE[0] + po + 4 * v);
-              cp_async16(ps + 3 * npsi + v, p.psiE[1] + po + 4 * v);
+              if (own[k] && ecoef) {
+                cp_async16(ps + 2 * npsi + v, p.psiE[0] + po + 4 * v);
+                cp_async16(ps + 3 * npsi + v, p.psiE[1] + po + 4 * v);
+              }
             }
           }
+        }
         }
       }
     };
@@ -365,7 +359,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       if (tid == 0) ok = ok && wait_deps(it);
       ok = bar_compute_and(NTc, ok);
       const int PLn = PL + 1 == X ? 0 : PL + 1;
-      if (ok && it <= X) issue(PL, PLn, it + 1, it, it == 0);
+      if (ok && it <= X) issue(PL, PLn, it + 1, it, it == 0, it >= 1);
       cp_async_commit();
       PL = PLn;
     }
@@ -399,7 +393,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         const int PLn = PL + 1 == X ? 0 : PL + 1;
         // loads of iteration i+D go to the slots freed by iteration i-1
         if (ok && i + D <= X)
-          issue(PL, PLn, se == 0 ? NE - 1 : se - 1, sh == 0 ? NH - 1 : sh - 1, false);
+          issue(PL, PLn, se == 0 ? NE - 1 : se - 1, sh == 0 ? NH - 1 : sh - 1, false, true);
         cp_async_commit();
         PL = PLn;
       }
@@ -408,7 +402,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         a[k][0] = an[k][0]; a[k][1] = an[k][1]; a[k][2] = an[k][2];
-        if (i < X) {
+        if (own[k] && i < X) {
           const size_t xy = (size_t)Pn * g.Y + yk[k];
           an[k][0] = __ldg(p.A + xy); an[k][1] = __ldg(p.A + XY + xy); an[k][2] = __ldg(p.A + 2 * XY + xy);
         }
@@ -438,12 +432,13 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 #pragma unroll
             for (int v = 0; v < VW; ++v) { ez_yp[v] = ez[1][v]; ex_yp[v] = ex[1][v]; }
           } else {
-            unpack(eC[2 * ring + nb_up], ez_yp, T()); unpack(eC[nb_up], ex_yp, T());
+            const int nb = doH[1] ? f[1] + Zq : f[1];
+            unpack(eC[2 * ring + nb], ez_yp, T()); unpack(eC[nb], ex_yp, T());
           }
           unpack(eN[ring + f[k]], ey_xp, T()); unpack(eN[2 * ring + f[k]], ez_xp, T());
 #pragma unroll
           for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
-          if (has_psi) { load_psi(pS + k * pstep, psx); load_psi(pS + k * pstep + npsi, psy); }
+          if (has_psi && doH[k]) { load_psi(pS + k * pstep, psx); load_psi(pS + k * pstep + npsi, psy); }
           float ex_top = __shfl_down_sync(0xffffffffu, ex[k][0], 1);
           float ey_top = __shfl_down_sync(0xffffffffu, ey[k][0], 1);
           if (fix_up) {
@@ -492,28 +487,28 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             unpack(sX[(k == 1 ? 2 * NTc : 4 * NTc) + tid - 1], tmp, T()); hy_bot = tmp[VW - 1];
           }
           if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
-          float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
-          if (k == 1) {
-#pragma unroll
-            for (int v = 0; v < VW; ++v) { hz_ym[v] = hz[0][v]; hx_ym[v] = hx[0][v]; }
-          } else {                                 // even column: previous thread's odd column
-            unpack(sX[nb_dn], hz_ym, T());
-            unpack(sX[NTc + nb_dn], hx_ym, T());
-          }
-#pragma unroll
-          for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
-          if (has_psi) { load_psi(pS + k * pstep + 2 * npsi, qsx); load_psi(pS + k * pstep + 3 * npsi, qsy); }
-          unpack(bC[f[k]], b0, T()); unpack(bC[ring + f[k]], b1, T()); unpack(bC[2 * ring + f[k]], b2, T());
-#pragma unroll
-          for (int v = 0; v < VW; ++v) {
-            const float hxz = (v > 0) ? hx[k][(v + VW - 1) % VW] : hx_bot;
-            const float hyz = (v > 0) ? hy[k][(v + VW - 1) % VW] : hy_bot;
-            e_cell(hx[k][v], hy[k][v], hz[k][v], hxz, hyz, hz_ym[v], hx_ym[v], hyp[k][v], hzp[k][v],
-                   ae[v], be[v], ike[v], a[k][0], a[k][1], a[k][2], b0[v], b1[v], b2[v], qsx[v],
-                   qsy[v], ex[k][v], ey[k][v], ez[k][v]);
-          }
-          if (own[k]) {                            // only the stores depend on ownership
+          if (own[k]) {
             const size_t offP = pP + coff[k];
+            float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
+            if (k == 1) {
+#pragma unroll
+              for (int v = 0; v < VW; ++v) { hz_ym[v] = hz[0][v]; hx_ym[v] = hx[0][v]; }
+            } else {                               // even column >= 2: previous thread's odd column
+              unpack(sX[tid - Zq], hz_ym, T());
+              unpack(sX[NTc + tid - Zq], hx_ym, T());
+            }
+#pragma unroll
+            for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
+            if (has_psi) { load_psi(pS + k * pstep + 2 * npsi, qsx); load_psi(pS + k * pstep + 3 * npsi, qsy); }
+            unpack(bC[f[k]], b0, T()); unpack(bC[ring + f[k]], b1, T()); unpack(bC[2 * ring + f[k]], b2, T());
+#pragma unroll
+            for (int v = 0; v < VW; ++v) {
+              const float hxz = (v > 0) ? hx[k][(v + VW - 1) % VW] : hx_bot;
+              const float hyz = (v > 0) ? hy[k][(v + VW - 1) % VW] : hy_bot;
+              e_cell(hx[k][v], hy[k][v], hz[k][v], hxz, hyz, hz_ym[v], hx_ym[v], hyp[k][v], hzp[k][v],
+                     ae[v], be[v], ike[v], a[k][0], a[k][1], a[k][2], b0[v], b1[v], b2[v], qsx[v],
+                     qsy[v], ex[k][v], ey[k][v], ez[k][v]);
+            }
             if (g.src_axis == 0 ? (P == sp0 || P == sp1) : src_thr[k])
               add_source<VW>(g, p.src, w0, w1, P, yk[k], q, ex[k], ey[k], ez[k]);
             store_vec<T, LD_CG>(p.Hs[wb][0] + offP, hx[k]);
@@ -607,9 +602,9 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
   int occ = 0;
-  if (cudaFuncSetAttribute(systolic2_kernel<T, D, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(systolic2_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            cfg->smem_bytes) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, systolic2_kernel<T, D, 0, 0>, cfg->threads,
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, systolic2_kernel<T, D>, cfg->threads,
                                                     cfg->smem_bytes) != cudaSuccess || occ < 1) {
     cudaGetLastError();
     *why = "kernel does not fit on an SM";
@@ -631,35 +626,22 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   return true;
 }
 
-template <typename T, int D, int NC, int ZQ>
-int systolic2_launch_inst(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
-                          cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(systolic2_kernel<T, D, NC, ZQ>,
+template <typename T, int D>
+int systolic2_launch_d(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
+                       cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(systolic2_kernel<T, D>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   Geom gg = g;
   Ptrs<T> pp = p;
   SystolicCfg cc = cfg;
   void* args[] = {&gg, &pp, &cc, &sync};
-  e = cudaLaunchCooperativeKernel((const void*)systolic2_kernel<T, D, NC, ZQ>,
+  e = cudaLaunchCooperativeKernel((const void*)systolic2_kernel<T, D>,
                                   dim3(cfg.stages * cfg.ntiles), dim3(cfg.threads), args,
                                   cfg.smem_bytes, st);
   if (e != cudaSuccess) return (int)e;
   systolic_check_kernel<<<1, 1, 0, st>>>(sync + (size_t)cfg.stages * cfg.ntiles * kSysFlagStride);
   return (int)cudaGetLastError();
-}
-
-// Geometry-specialised instances exist for Zq = 32 (Z = 128 fp32 / 256 fp16), the height of
-// every BASELINE configuration, at the tile widths the planner picks; anything else runs the
-// generic instance.
-template <typename T, int D>
-int systolic2_launch_d(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
-                       cudaStream_t st) {
-  if (D == 1 && g.Zq == 32 && !getenv("B200FDTD_GENERIC")) {
-    if (cfg.tile_y == 12) return systolic2_launch_inst<T, D, 14, 32>(g, p, cfg, sync, st);
-    if (cfg.tile_y == 10) return systolic2_launch_inst<T, D, 12, 32>(g, p, cfg, sync, st);
-  }
-  return systolic2_launch_inst<T, D, 0, 0>(g, p, cfg, sync, st);
 }
 
 }  // namespace b200
