@@ -72,8 +72,10 @@ enum {
   B200FDTD_KERNEL_TWOPASS = 1,  /* one H launch + one E launch per step, in place          */
   B200FDTD_KERNEL_SYSTOLIC = 2, /* one persistent launch: fused H+E x-sweep, L2-pipelined
                                    stages, operands staged through registers               */
-  B200FDTD_KERNEL_SYSTOLIC_ASYNC = 3 /* same protocol; operands staged through a cp.async
-                                   shared-memory ring, dedicated sync warp (the fast path)  */
+  B200FDTD_KERNEL_SYSTOLIC_ASYNC = 3, /* same protocol; operands staged through a cp.async
+                                   shared-memory ring, service warp for the protocol       */
+  B200FDTD_KERNEL_SYSTOLIC_TMA = 4 /* same protocol; operands staged by TMA bulk copies
+                                   (cp.async.bulk + mbarrier) issued by the service warp    */
 };
 
 /* Static description of one engine call (everything that is a python scalar/tuple at

@@ -18,6 +18,7 @@
 #include "fdtd_common.cuh"
 #include "kernels_systolic.cuh"
 #include "kernels_systolic2.cuh"
+#include "kernels_systolic3.cuh"
 #include "kernels_twopass.cuh"
 
 namespace b200 {
@@ -69,7 +70,7 @@ static int validate(const b200fdtd_desc* d) {
     return fail(B200FDTD_EINVAL, "output_steps (%d,%d,%d) outside [0,tt=%d)", d->out_start,
                 d->out_stop, d->out_step, d->tt);
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
-  if (d->kernel < 0 || d->kernel > 3) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  if (d->kernel < 0 || d->kernel > 4) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
   return B200FDTD_OK;
 }
 
@@ -108,7 +109,8 @@ struct Plan {
 };
 
 static bool is_systolic(int k) {
-  return k == B200FDTD_KERNEL_SYSTOLIC || k == B200FDTD_KERNEL_SYSTOLIC_ASYNC;
+  return k == B200FDTD_KERNEL_SYSTOLIC || k == B200FDTD_KERNEL_SYSTOLIC_ASYNC ||
+         k == B200FDTD_KERNEL_SYSTOLIC_TMA;
 }
 
 static int device_props(int* sms, int* l2_bytes) {
@@ -131,6 +133,17 @@ static bool configure_async(const Geom& g, const b200fdtd_desc* d, int depth, in
   return false;
 }
 
+template <typename T>
+static bool configure_tma(const Geom& g, const b200fdtd_desc* d, int depth, int sms, int l2,
+                          SystolicCfg* cfg, std::string* why) {
+  switch (depth) {
+    case 1: return systolic3_configure_d<T, 1>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
+    case 2: return systolic3_configure_d<T, 2>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
+  }
+  *why = "prefetch must be 1 or 2";
+  return false;
+}
+
 // AUTO: cp.async-staged systolic kernel (prefetch distance 1 measured fastest: a deeper ring
 // only shrinks the tile), else the register-staged one, else the per-step kernels.
 template <typename T>
@@ -142,6 +155,13 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   int rc = device_props(&sms, &l2);
   if (rc) return rc;
   std::string why;
+  if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_TMA) {
+    const int depth = d->prefetch > 0 ? d->prefetch : 1;
+    if (!configure_tma<T>(g, d, depth, sms, l2, &plan->sys, &why))
+      return fail(B200FDTD_EUNSUPPORTED, "systolic_tma kernel unavailable: %s", why.c_str());
+    plan->depth = depth;
+    return B200FDTD_OK;
+  }
   if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {
     const int depth = d->prefetch > 0 ? d->prefetch : 1;
     if (configure_async<T>(g, d, depth, sms, l2, &plan->sys, &why)) {
@@ -312,6 +332,9 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
     unsigned* sync = reinterpret_cast<unsigned*>(ws + w.sync);
     int rc;
     if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
+    else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_TMA)
+      rc = plan.depth == 2 ? systolic3_launch_d<T, 2>(g, p, plan.sys, sync, st)
+                           : systolic3_launch_d<T, 1>(g, p, plan.sys, sync, st);
     else if (plan.depth == 1) rc = systolic2_launch_d<T, 1>(g, p, plan.sys, sync, st);
     else if (plan.depth == 2) rc = systolic2_launch_d<T, 2>(g, p, plan.sys, sync, st);
     else rc = systolic2_launch_d<T, 3>(g, p, plan.sys, sync, st);

@@ -25,7 +25,7 @@ from tests.problems import random_problem, rel_l2
 pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "engine_golden.npz"))
-KERNELS = ["twopass", "systolic", "systolic_async"]
+KERNELS = ["twopass", "systolic", "systolic_async", "systolic_tma"]
 FP32_TOL = 1e-5
 
 
@@ -93,6 +93,16 @@ def test_systolic_async_tilings(tile_y, stages, prefetch):
   np.testing.assert_array_equal(out, want)
 
 
+@pytest.mark.parametrize("prefetch", [1, 2])
+@pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (6, 3), (4, 40)])
+def test_systolic_tma_tilings(tile_y, stages, prefetch):
+  kw = random_problem(domain=(11, 23, 16), axis=1, pml=(4, 4), tt=45, seed=13,
+                      output_steps=(20, 45, 6))
+  want = fdtd_c.fdtdz(**kw)
+  out = run_gpu(kw, kernel="systolic_tma", tile_y=tile_y, stages=stages, prefetch=prefetch)
+  np.testing.assert_array_equal(out, want)
+
+
 @pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (5, 3), (14, 7), (4, 40)])
 def test_systolic_tilings(tile_y, stages):
   """Every tiling / pipeline depth must give the same bits (many stages on a short x extent
@@ -154,6 +164,7 @@ def test_schedule_selection_and_linearity_large():
   b = run_gpu(kw, kernel="systolic")
   np.testing.assert_array_equal(a, b)
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_async"))
+  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_tma"))
   assert np.isfinite(a).all() and np.abs(a).max() > 0
   kw2 = dict(kw); kw2["output_steps"] = (5, 16, 10)
   np.testing.assert_array_equal(run_gpu(kw2), a[1:4:2])
