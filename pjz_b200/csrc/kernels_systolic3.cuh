@@ -157,112 +157,138 @@ systolic3_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     unsigned avail = 0, next = 0;                  // cached counters
     unsigned published = 0;
 
-    for (unsigned G = 0; G < total_iters + (unsigned)D + 1u; ++G) {
-      // ---- (1) iteration G-D-1 is finished by every compute warp: its ring stage is free and
-      //          its stores are issued -> publish it.
-      if (G >= (unsigned)D + 1u) {
-        const unsigned Gd = G - (unsigned)D - 1u;  // finished iteration
-        mbar_wait(&empty_bar[Gd % NH], (Gd / NH) & 1u, status);
-        const unsigned sw = Gd / sweep_iters, it = Gd % sweep_iters;
-        if (it >= 1 && lane == 0) {
-          const unsigned prog = sw * (unsigned)X + it;   // cumulative finished sweep indices
-          if (prog != published) { st_release_u32(my_prog, prog); published = prog; }
-        }
-      }
-      if (G >= total_iters) continue;
-      // ---- (2) dependencies of group G (the k+3 rule and the max_lead throttle)
-      const unsigned sw = G / sweep_iters, it = G % sweep_iters;
-      const int n = j + (int)sw * S;
-      const unsigned base_prev = (j > 0 ? sw : sw - 1u) * (unsigned)X;
-      const unsigned base_mine = sw * (unsigned)X;
-      const unsigned need = n > 0 ? base_prev + (unsigned)min((int)it + 2, X) : 0u;
-      const int lead = min((int)it, X) - 1 - cfg.max_lead;
-      const unsigned need_next = (n + 1 < g.tt && j + 1 < S && lead > 0) ? base_mine + (unsigned)lead : 0u;
-      if (avail < need || next < need_next) {
-        unsigned long long t0 = 0;
-        unsigned spins = 0;
-        while (true) {
-          unsigned v = 0xffffffffu;
-          if (lane < 5) v = ld_relaxed_gpu_u32(watch);
-          const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
-                         v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
-                         v4 = __shfl_sync(0xffffffffu, v, 4);
-          avail = min(v0, min(v1, v2));
-          next = v3;
-          if (v4 != 0) __trap();                   // another CTA gave up
-          if (avail >= need && next >= need_next) break;
-          if ((++spins & 255u) == 0) {
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 5000000000ull) { atomicCAS(status, 0u, 1u + blockIdx.x); __trap(); }
+    // Non-blocking event loop.  Gi = next group to issue, Gp = next iteration whose completion
+    // is to be published.  Priority: (a) issue a group as soon as its ring stage is free and its
+    // dependencies hold (this is what keeps the compute warps fed), (b) publish finished
+    // iterations, (c) poll the neighbours' counters.  Never blocking in one duty while another
+    // is pending is also what makes short domains (X < 3*stages) deadlock-free: a CTA keeps
+    // publishing its finished planes while it waits for its own predecessor.
+    unsigned Gi = 0, Gp = 0;
+    unsigned long long idle_since = 0;
+    while (Gp < total_iters) {
+      bool progress = false;
+      // ---- (a) issue group Gi: needs iteration Gi-D-1 finished (Gi <= Gp + D) and its deps
+      if (Gi < total_iters && Gi <= Gp + (unsigned)D) {
+        const unsigned G = Gi;
+        const unsigned sw = G / sweep_iters, it = G % sweep_iters;
+        const int n = j + (int)sw * S;
+        const unsigned base_prev = (j > 0 ? sw : sw - 1u) * (unsigned)X;
+        const unsigned base_mine = sw * (unsigned)X;
+        const unsigned need = n > 0 ? base_prev + (unsigned)min((int)it + 2, X) : 0u;
+        const int lead = min((int)it, X) - 1 - cfg.max_lead;
+        const unsigned need_next =
+            (n + 1 < g.tt && j + 1 < S && lead > 0) ? base_mine + (unsigned)lead : 0u;
+        if (avail >= need && next >= need_next) {
+          // lanes 0..15 each own one array (E0-2 @P+1, H0-2, B0-2, psi x4 @P, and E0-2 @P for
+          // the first iteration of a sweep) and issue its bulk copies.
+          const int rb = n & 1;
+          const int P = wrapi(n % X - 1 + (int)it, X), Pn = P + 1 == X ? 0 : P + 1;
+          const size_t pP = (size_t)P * g.P, pN = (size_t)Pn * g.P;
+          unsigned long long* bar = &full_bar[G % NH];
+          const bool first = it == 0;
+          if (lane == 0) {
+            fence_proxy_async();                   // other CTAs' generic-proxy stores -> TMA reads
+            mbar_expect_tx(bar, grpB + (first ? (unsigned)ncols * 3u * colB : 0u));
           }
+          __syncwarp();
+          const char* src = nullptr;               // start of the array's plane
+          float4* dst = nullptr;                   // ring row 0 of the array
+          unsigned cbytes = colB;                  // bytes per column
+          int cunits = Zq;                         // float4 per column in the ring
+          const int a = lane;
+          if (a < 3) {
+            src = reinterpret_cast<const char*>(p.Es[rb][a] + pN);
+            dst = sE + ((G + 1u) % NE) * eslot + a * ring;
+          } else if (a < 6) {
+            src = reinterpret_cast<const char*>(p.Hs[rb][a - 3] + pP);
+            dst = sH + (G % NH) * eslot + (a - 3) * ring;
+          } else if (a < 9) {
+            src = reinterpret_cast<const char*>(p.B[a - 6] + pP);
+            dst = sB + (G % NH) * eslot + (a - 6) * ring;
+          } else if (a < 13) {
+            if (g.npg > 0) {
+              const size_t po = (size_t)P * g.Y * g.npg * VW;
+              const float* base = a < 11 ? p.psiHs[rb][a - 9] : p.psiE[a - 11];
+              src = reinterpret_cast<const char*>(base + po);
+              dst = sP + (G % NH) * pslot + (a - 9) * npsi;
+              cbytes = colP;
+              cunits = g.npg * PV;
+            }
+          } else if (a < 16 && first) {
+            src = reinterpret_cast<const char*>(p.Es[rb][a - 13] + pP);
+            dst = sE + (G % NE) * eslot + (a - 13) * ring;
+          }
+          if (src != nullptr) {
+            // interior run of columns [ca, cb), then the (at most two) wrapped halo columns
+            tma_load_1d(dst + ca * cunits, src + (size_t)(y0 - 1 + ca) * cbytes,
+                        (unsigned)(cb - ca) * cbytes, bar);
+            if (ca == 1) tma_load_1d(dst, src + (size_t)(g.Y - 1) * cbytes, cbytes, bar);
+            if (cb == ncols - 1) tma_load_1d(dst + (ncols - 1) * cunits, src, cbytes, bar);
+          }
+          ++Gi;
+          progress = true;
+          // L2 prefetch of the planes of groups [Gi, Gi + pf_ahead)
+          if (cfg.pf_ahead > 0 && lane >= 16 && lane < 25) {
+            if (pf_done < Gi) pf_done = Gi;
+            for (; pf_done < Gi + (unsigned)cfg.pf_ahead && pf_done < total_iters; ++pf_done) {
+              const unsigned sw2 = pf_done / sweep_iters, it2 = pf_done % sweep_iters;
+              const int n2 = j + (int)sw2 * S, rb2 = n2 & 1;
+              const int P2 = wrapi(n2 % X - 1 + (int)it2, X), Pn2 = P2 + 1 == X ? 0 : P2 + 1;
+              const int b = lane - 16;
+              const T* base;
+              int plane;
+              if (b < 3) { base = p.Es[rb2][b]; plane = Pn2; }
+              else if (b < 6) { base = p.Hs[rb2][b - 3]; plane = P2; }
+              else { base = p.B[b - 6]; plane = P2; }
+              prefetch_l2_bulk(base + (size_t)plane * g.P + pf_off, pf_bytes);
+            }
+          }
+          __syncwarp();
+          continue;                                // try to issue the next group right away
         }
       }
-      // ---- (3) issue group G: lanes 0..15 each own one array (E0-2 @P+1, H0-2, B0-2, psi x4 @P,
-      //          and E0-2 @P for the first iteration of a sweep) and issue its bulk copies.
+      // ---- (b) publish finished iterations (their stores are issued; st.release = fence + store)
+      if (mbar_try_wait(&empty_bar[Gp % NH], (Gp / NH) & 1u)) {
+        // drain every iteration that is already finished, publish the newest count once
+        unsigned prog = published;
+        do {
+          const unsigned sw = Gp / sweep_iters, it = Gp % sweep_iters;
+          if (it >= 1) prog = sw * (unsigned)X + it;     // cumulative finished sweep indices
+          ++Gp;
+          // (testing phase Gp/NH of a stage is alias-free: its previous phase, iteration Gp-NH,
+          // is already known to be complete)
+        } while (Gp < total_iters && mbar_try_wait(&empty_bar[Gp % NH], (Gp / NH) & 1u));
+        if (prog != published) {
+          if (lane == 0) st_release_u32(my_prog, prog);
+          published = prog;
+        }
+        progress = true;
+        continue;
+      }
+      // ---- (c) refresh the neighbours' counters
       {
-        const int rb = n & 1;
-        const int P = wrapi(n % X - 1 + (int)it, X), Pn = P + 1 == X ? 0 : P + 1;
-        const size_t pP = (size_t)P * g.P, pN = (size_t)Pn * g.P;
-        unsigned long long* bar = &full_bar[G % NH];
-        const bool first = it == 0;
-        if (lane == 0) {
-          fence_proxy_async();                     // other CTAs' generic-proxy stores -> TMA reads
-          mbar_expect_tx(bar, grpB + (first ? (unsigned)ncols * 3u * colB : 0u));
-        }
-        __syncwarp();
-        const char* src = nullptr;                 // start of the array's plane
-        float4* dst = nullptr;                     // ring row 0 of the array
-        unsigned cbytes = colB;                    // bytes per column
-        int cunits = Zq;                           // float4 per column in the ring
-        const int a = lane;
-        if (a < 3) {
-          src = reinterpret_cast<const char*>(p.Es[rb][a] + pN);
-          dst = sE + ((G + 1u) % NE) * eslot + a * ring;
-        } else if (a < 6) {
-          src = reinterpret_cast<const char*>(p.Hs[rb][a - 3] + pP);
-          dst = sH + (G % NH) * eslot + (a - 3) * ring;
-        } else if (a < 9) {
-          src = reinterpret_cast<const char*>(p.B[a - 6] + pP);
-          dst = sB + (G % NH) * eslot + (a - 6) * ring;
-        } else if (a < 13) {
-          if (g.npg > 0) {
-            const size_t po = (size_t)P * g.Y * g.npg * VW;
-            const float* base = a < 11 ? p.psiHs[rb][a - 9] : p.psiE[a - 11];
-            src = reinterpret_cast<const char*>(base + po);
-            dst = sP + (G % NH) * pslot + (a - 9) * npsi;
-            cbytes = colP;
-            cunits = g.npg * PV;
-          }
-        } else if (a < 16 && first) {
-          src = reinterpret_cast<const char*>(p.Es[rb][a - 13] + pP);
-          dst = sE + (G % NE) * eslot + (a - 13) * ring;
-        }
-        if (src != nullptr) {
-          // interior run of columns [ca, cb), then the (at most two) wrapped halo columns
-          tma_load_1d(dst + ca * cunits, src + (size_t)(y0 - 1 + ca) * cbytes,
-                      (unsigned)(cb - ca) * cbytes, bar);
-          if (ca == 1) tma_load_1d(dst, src + (size_t)(g.Y - 1) * cbytes, cbytes, bar);
-          if (cb == ncols - 1) tma_load_1d(dst + (ncols - 1) * cunits, src, cbytes, bar);
+        unsigned v = 0xffffffffu;
+        if (lane < 5) v = ld_relaxed_gpu_u32(watch);
+        const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
+                       v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
+                       v4 = __shfl_sync(0xffffffffu, v, 4);
+        const unsigned na = min(v0, min(v1, v2));
+        if (na != avail || v3 != next) progress = true;
+        avail = na;
+        next = v3;
+        if (v4 != 0) __trap();                     // another CTA gave up
+      }
+      // ---- watchdog: nothing moved for 5 s -> report and trap (never hang)
+      if (progress) {
+        idle_since = 0;
+      } else {
+        const unsigned long long now = globaltimer_ns();
+        if (idle_since == 0) idle_since = now;
+        else if (now - idle_since > 5000000000ull) {
+          atomicCAS(status, 0u, 1u + blockIdx.x);
+          __trap();
         }
       }
-      // ---- (4) L2 prefetch of the planes of groups [G+1, G+1+pf_ahead)
-      if (cfg.pf_ahead > 0 && lane >= 8 && lane < 17) {
-        if (pf_done < G + 1u) pf_done = G + 1u;
-        for (; pf_done < G + 1u + (unsigned)cfg.pf_ahead && pf_done < total_iters; ++pf_done) {
-          const unsigned sw2 = pf_done / sweep_iters, it2 = pf_done % sweep_iters;
-          const int n2 = j + (int)sw2 * S, rb2 = n2 & 1;
-          const int P2 = wrapi(n2 % X - 1 + (int)it2, X), Pn2 = P2 + 1 == X ? 0 : P2 + 1;
-          const int a = lane - 8;
-          const T* base;
-          int plane;
-          if (a < 3) { base = p.Es[rb2][a]; plane = Pn2; }
-          else if (a < 6) { base = p.Hs[rb2][a - 3]; plane = P2; }
-          else { base = p.B[a - 6]; plane = P2; }
-          prefetch_l2_bulk(base + (size_t)plane * g.P + pf_off, pf_bytes);
-        }
-      }
-      __syncwarp();
     }
     return;
   }
