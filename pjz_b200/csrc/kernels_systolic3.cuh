@@ -163,12 +163,13 @@ systolic3_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     // iterations, (c) poll the neighbours' counters.  Never blocking in one duty while another
     // is pending is also what makes short domains (X < 3*stages) deadlock-free: a CTA keeps
     // publishing its finished planes while it waits for its own predecessor.
-    unsigned Gi = 0, Gp = 0;
+    unsigned Gi = 0, Gp = 0, prog_new = 0, naps = 0;
     unsigned long long idle_since = 0;
     while (Gp < total_iters) {
       bool progress = false;
       // ---- (a) issue group Gi: needs iteration Gi-D-1 finished (Gi <= Gp + D) and its deps
-      if (Gi < total_iters && Gi <= Gp + (unsigned)D) {
+      const bool ring_free = Gi < total_iters && Gi <= Gp + (unsigned)D;
+      if (ring_free) {
         const unsigned G = Gi;
         const unsigned sw = G / sweep_iters, it = G % sweep_iters;
         const int n = j + (int)sw * S;
@@ -244,29 +245,32 @@ systolic3_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             }
           }
           __syncwarp();
+          idle_since = 0;
           continue;                                // try to issue the next group right away
         }
       }
-      // ---- (b) publish finished iterations (their stores are issued; st.release = fence + store)
+      // ---- (b) note finished iterations (cheap: frees their ring stage for the next issue)
       if (mbar_try_wait(&empty_bar[Gp % NH], (Gp / NH) & 1u)) {
-        // drain every iteration that is already finished, publish the newest count once
-        unsigned prog = published;
         do {
           const unsigned sw = Gp / sweep_iters, it = Gp % sweep_iters;
-          if (it >= 1) prog = sw * (unsigned)X + it;     // cumulative finished sweep indices
+          if (it >= 1) prog_new = sw * (unsigned)X + it;  // cumulative finished sweep indices
           ++Gp;
           // (testing phase Gp/NH of a stage is alias-free: its previous phase, iteration Gp-NH,
           // is already known to be complete)
         } while (Gp < total_iters && mbar_try_wait(&empty_bar[Gp % NH], (Gp / NH) & 1u));
-        if (prog != published) {
-          if (lane == 0) st_release_u32(my_prog, prog);
-          published = prog;
-        }
-        progress = true;
+        idle_since = 0;
+        continue;                                  // give (a) the first chance
+      }
+      // ---- (c) publish (st.release.gpu = fence + store, ~1 us): only when nothing can be issued
+      if (prog_new != published) {
+        if (lane == 0) st_release_u32(my_prog, prog_new);
+        published = prog_new;
+        idle_since = 0;
         continue;
       }
-      // ---- (c) refresh the neighbours' counters
-      {
+      // ---- (d) blocked on dependencies: refresh the neighbours' counters; otherwise the compute
+      //          warps are simply busy -> back off briefly
+      if (ring_free) {
         unsigned v = 0xffffffffu;
         if (lane < 5) v = ld_relaxed_gpu_u32(watch);
         const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
@@ -277,6 +281,9 @@ systolic3_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         avail = na;
         next = v3;
         if (v4 != 0) __trap();                     // another CTA gave up
+      } else {
+        __nanosleep(32);
+        if ((++naps & 4095u) != 0) continue;       // look at the clock only now and then
       }
       // ---- watchdog: nothing moved for 5 s -> report and trap (never hang)
       if (progress) {
