@@ -297,6 +297,7 @@ systolic3_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         }
       }
     }
+    if (prog_new != published && lane == 0) st_release_u32(my_prog, prog_new);   // final count
     return;
   }
 
