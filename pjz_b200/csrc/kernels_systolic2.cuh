@@ -373,6 +373,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
     int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
     int se = 0, sh = 0;                            // ring slots of E[P] and H/B/psi[P]
 
+#pragma unroll 2
     for (int i = 0; i <= X && ok; ++i) {
       const bool real = i >= 1;
       const int Pn = P + 1 == X ? 0 : P + 1;
