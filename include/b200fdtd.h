@@ -146,6 +146,36 @@ void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
  * launches_per_run, l2_window_bytes>>20}.  */
 int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info);
 
+
+/* ---- Stepping sessions ---------------------------------------------------------------------------
+ * For callers that drive the time loop themselves -- the x-slab domain decomposition of
+ * pjz_b200/_decomp.py exchanges halo planes between GPUs after every half-step.  A session
+ * binds a descriptor, the input arrays and a caller-owned workspace (no internal allocation),
+ * prepares the coefficients, and then advances one half-step per call with the per-step
+ * kernels, in place.  Between calls the caller may read and write field planes directly in the
+ * workspace (b200fdtd_session_layout says where they are).  Everything is ordered on the
+ * stream passed to each call.  There is no reference counterpart (fdtd-z is single-GPU). */
+typedef struct b200fdtd_session b200fdtd_session;
+
+size_t b200fdtd_session_workspace_bytes(const b200fdtd_desc* desc);
+
+int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs,
+                            void* const* outputs, void* workspace, size_t workspace_bytes,
+                            void* stream, b200fdtd_session** session);
+
+/* H^{n+1/2} <- H^{n-1/2}, E^n  (all X planes of the session's domain). */
+int b200fdtd_session_step_h(b200fdtd_session* session, void* stream);
+
+/* E^{n+1} <- E^n, H^{n+1/2}; adds the source of step n; writes the snapshot if n is an output step. */
+int b200fdtd_session_step_e(b200fdtd_session* session, int n, void* stream);
+
+/* info[8] = {byte offset of Ex, byte offset of Hx, bytes between components, bytes per x-plane,
+ *            padded z extent Zp, bytes per element, X, Y}: component c of E lives at
+ *            workspace + info[0] + c*info[2], laid out [X][Y][Zp]. */
+int b200fdtd_session_layout(const b200fdtd_session* session, int64_t* info);
+
+void b200fdtd_session_destroy(b200fdtd_session* session);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <new>
 #include <string>
 
 #include "fdtd_common.cuh"
@@ -284,11 +285,14 @@ __global__ void prep_b_kernel(Geom g, const float* __restrict__ eps, const float
 
 // ---- the run ----------------------------------------------------------------------------------
 
+// Binds the workspace regions and the caller's arrays into `p`, zeroes the state and runs the
+// coefficient-preparation kernels (all stream-ordered).
 template <typename T>
-static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, const Workspace& w,
-                     const void* const* in, void* const* out, char* ws, cudaStream_t st) {
+static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace& w,
+                         const void* const* in, void* const* out, char* ws, cudaStream_t st,
+                         Ptrs<T>* pp) {
   constexpr int VW = VecTraits<T>::VW;
-  Ptrs<T> p;
+  Ptrs<T>& p = *pp;
   T* fields = reinterpret_cast<T*>(ws + w.fields);
   T* fields2 = reinterpret_cast<T*>(ws + w.fields2);
   T* B = reinterpret_cast<T*>(ws + w.B);
@@ -326,7 +330,15 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
   prep_b_kernel<T><<<148 * 8, 256, 0, st>>>(
       g, static_cast<const float*>(in[B200FDTD_IN_EPSILON]), S, B);
   CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
 
+template <typename T>
+static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, const Workspace& w,
+                     const void* const* in, void* const* out, char* ws, cudaStream_t st) {
+  Ptrs<T> p;
+  int prc = prepare_typed<T>(d, g, w, in, out, ws, st, &p);
+  if (prc) return prc;
   if (g.tt == 0) return B200FDTD_OK;
   if (is_systolic(plan.kernel)) {
     unsigned* sync = reinterpret_cast<unsigned*>(ws + w.sync);
@@ -521,5 +533,90 @@ int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
   }
   return B200FDTD_OK;
 }
+
+
+// ---- stepping sessions (host-driven time loops: domain decomposition with halo exchange) ------
+
+struct b200fdtd_session {
+  b200fdtd_desc d;
+  Geom g;
+  Workspace w;
+  char* ws;
+  bool reduced;
+  Ptrs<float> pf;
+  Ptrs<__half> ph;
+  dim3 grid;
+};
+
+size_t b200fdtd_session_workspace_bytes(const b200fdtd_desc* desc) {
+  if (validate(desc)) return 0;
+  const Geom g = make_geom(desc);
+  return carve(g, desc->use_reduced_precision != 0, false, nullptr).total;
+}
+
+int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs,
+                            void* const* outputs, void* workspace, size_t workspace_bytes,
+                            void* stream, b200fdtd_session** session) {
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!session) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (!inputs || !outputs || !workspace) return fail(B200FDTD_EINVAL, "inputs/outputs/workspace is NULL");
+  for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i)
+    if (!inputs[i]) return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i);
+  if (num_outputs(desc) > 0 && !outputs[0]) return fail(B200FDTD_EINVAL, "outputs[0] is NULL");
+  const Geom g = make_geom(desc);
+  if (g.X > 65535) return fail(B200FDTD_EUNSUPPORTED, "sessions support X <= 65535");
+  const Workspace w = carve(g, desc->use_reduced_precision != 0, false, nullptr);
+  if (workspace_bytes < w.total)
+    return fail(B200FDTD_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
+                workspace_bytes);
+  if ((uintptr_t)workspace % 256 != 0) return fail(B200FDTD_EINVAL, "workspace must be 256-byte aligned");
+  b200fdtd_session* s = new (std::nothrow) b200fdtd_session();
+  if (!s) return fail(B200FDTD_EINVAL, "out of host memory");
+  s->d = *desc; s->g = g; s->w = w; s->ws = static_cast<char*>(workspace);
+  s->reduced = desc->use_reduced_precision != 0;
+  s->grid = dim3((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads, g.X);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = s->reduced ? prepare_typed<__half>(desc, g, w, inputs, outputs, s->ws, st, &s->ph)
+                  : prepare_typed<float>(desc, g, w, inputs, outputs, s->ws, st, &s->pf);
+  if (rc) { delete s; return rc; }
+  *session = s;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_step_h(b200fdtd_session* s, void* stream) {
+  if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s->reduced) twopass_h_kernel<__half><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->ph);
+  else twopass_h_kernel<float><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->pf);
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_step_e(b200fdtd_session* s, int n, void* stream) {
+  if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (n < 0 || n >= s->g.tt) return fail(B200FDTD_EINVAL, "step %d outside [0,%d)", n, s->g.tt);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s->reduced) twopass_e_kernel<__half><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->ph, n);
+  else twopass_e_kernel<float><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->pf, n);
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_layout(const b200fdtd_session* s, int64_t* info) {
+  if (!s || !info) return fail(B200FDTD_EINVAL, "session/info is NULL");
+  const int64_t el = s->reduced ? 2 : 4;
+  info[0] = (int64_t)s->w.fields;                 // byte offset of Ex in the workspace
+  info[1] = (int64_t)s->w.fields + 3 * s->g.N * el;   // byte offset of Hx
+  info[2] = s->g.N * el;                          // bytes between components
+  info[3] = s->g.P * el;                          // bytes per x-plane
+  info[4] = (int64_t)s->g.Zp;                     // padded z extent (elements per column)
+  info[5] = el;                                   // bytes per element (4 fp32, 2 fp16 storage)
+  info[6] = s->g.X;
+  info[7] = s->g.Y;
+  return B200FDTD_OK;
+}
+
+void b200fdtd_session_destroy(b200fdtd_session* s) { delete s; }
 
 }  // extern "C"

@@ -1,0 +1,175 @@
+"""x-slab domain decomposition (pjz_b200/_decomp.py).
+
+CPU: the orchestration (slab inputs, ghost planes, halo exchange order, source ownership,
+snapshot cropping) is driven with an ORACLE-backed slab engine over gloo, world sizes 1-3, and
+must reproduce the single-domain oracle run EXACTLY.  GPU: the same driver over the C ABI's
+stepping session must be bit-identical to the one-call engine (1 GPU, self-wrapped ghosts; and
+2 ranks when two GPUs are present).
+"""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleSlab:
+  """Slab engine backed by the float64 NumPy spec (tests only)."""
+
+  def __init__(self, loc):
+    from oracle import fdtd_numpy as spec
+    self.spec = spec
+    self.loc = loc
+    eps = np.asarray(loc["epsilon"], np.float32)
+    self.st = spec.State(eps, loc["dt"], loc["absorption_mask"], loc["pml_kappa"],
+                         loc["pml_sigma"], loc["pml_alpha"], loc["pml_widths"], loc["offset"],
+                         np.float64)
+    self.sf = np.asarray(loc["source_field"], np.float64)
+    self.wf = np.asarray(loc["source_waveform"], np.float32).astype(np.float64)
+    self.axis = spec.source_axis(self.sf)
+    self.outs = list(range(*loc["output_steps"]))
+    _, xx, yy, zz = eps.shape
+    self.sub = (xx, yy, zz)
+    self.out = np.zeros((len(self.outs), 3, xx, yy, zz), np.float32)
+    self.E = torch.from_numpy(self.st.E)      # shared memory views (3, X, Y, Z)
+    self.H = torch.from_numpy(self.st.H)
+
+  def step_h(self):
+    self.st.step_h()
+
+  def step_e(self, n):
+    self.st.step_e()
+    self.st.add_source(self.sf, self.wf[n], self.loc["source_position"], self.axis)
+    if n in self.outs:
+      ox, oy, oz = self.loc["offset"]
+      xx, yy, zz = self.sub
+      self.out[self.outs.index(n)] = self.st.E[:, ox:ox + xx, oy:oy + yy, oz:oz + zz]
+
+  def snapshots(self):
+    return self.out
+
+
+def _problems():
+  from tests.problems import random_problem
+  return [
+      random_problem(domain=(12, 10, 8), axis=0, pml=(2, 3), tt=14, seed=21, output_steps=(5, 14, 4),
+                     src_pos=4),
+      random_problem(domain=(11, 9, 8), axis=0, pml=(2, 2), tt=12, seed=22, output_steps=(3, 12, 3),
+                     src_pos=6),                 # plane 6 / 5 straddle the 2-rank cut (5|6)
+      random_problem(domain=(10, 8, 8), axis=1, pml=(0, 3), tt=12, seed=23, output_steps=(0, 12, 5)),
+      random_problem(domain=(9, 10, 12), axis=2, pml=(3, 3), tt=12, seed=24, output_steps=(11, 12, 1)),
+  ]
+
+
+def _worker(rank, world, port, out_path):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from pjz_b200._decomp import fdtdz_decomposed
+  outs = [fdtdz_decomposed(**kw, make_slab=OracleSlab).numpy() for kw in _problems()]
+  if rank == 0:
+    np.savez(out_path, *outs)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_decomposed_oracle_matches_single_domain(world, tmp_path):
+  from oracle import fdtd_numpy
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "dd.npz")
+  mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+  got = np.load(out)
+  for i, kw in enumerate(_problems()):
+    np.testing.assert_array_equal(got[f"arr_{i}"], fdtd_numpy.fdtdz(**kw))
+
+
+def test_single_rank_wraps_onto_itself():
+  from oracle import fdtd_numpy
+  from pjz_b200._decomp import fdtdz_decomposed
+  for kw in _problems():
+    out = fdtdz_decomposed(**kw, make_slab=OracleSlab).numpy()
+    np.testing.assert_array_equal(out, fdtd_numpy.fdtdz(**kw))
+
+
+def test_slab_inputs():
+  from pjz_b200._decomp import local_problem, slab_bounds
+  from tests.problems import random_problem
+  kw = random_problem(domain=(11, 9, 8), sub=(5, 4, 3), offset=(4, 2, 1), axis=0, tt=6, seed=1,
+                      src_pos=6)
+  assert [slab_bounds(11, 3, r) for r in range(3)] == [(0, 3), (3, 7), (7, 11)]
+  loc, nloc, crop = local_problem(kw, 1, 3)       # owns planes 3..6, ghosts 2 and 7
+  assert nloc == 4 and loc["epsilon"].shape == (3, 6, 4, 3) and loc["offset"] == (0, 2, 1)
+  assert loc["absorption_mask"].shape == (3, 6, 9)
+  # epsilon is edge-replicated in x: local planes 0..2 (global 2,3,4) all see sub-volume plane 0
+  np.testing.assert_array_equal(loc["epsilon"][:, 0], kw["epsilon"][:, 0])
+  np.testing.assert_array_equal(loc["epsilon"][:, 2], kw["epsilon"][:, 0])
+  np.testing.assert_array_equal(loc["epsilon"][:, 4], kw["epsilon"][:, 2])
+  # source plane 6 is local plane 4 (owned); plane 5 (channel 1) is local 3 (owned)
+  assert loc["source_position"] == 4 and loc["source_waveform"].any()
+  assert crop == (2, 5, 0, 3)                     # global planes 4..6 -> local 2..4, out 0..2
+  loc2, nloc2, crop2 = local_problem(kw, 2, 3)    # owns 7..10: plane 6 is its low ghost
+  assert not loc2["source_waveform"].any()
+  assert crop2 == (1, 3, 3, 5)                    # global 7..8 -> local 1..2, out 3..4
+  with pytest.raises(ValueError):
+    local_problem(kw, 0, 12)
+
+
+# ---- GPU ------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_session_driver_equals_one_call_engine(built):
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import fdtdz_decomposed
+  from tests.problems import random_problem
+  for axis, reduced in [(0, False), (1, False), (2, False), (0, True)]:
+    kw = random_problem(domain=(20, 18, 40), axis=axis, pml=(5, 6), tt=30, seed=60 + axis,
+                        output_steps=(10, 30, 7), reduced=reduced, src_pos=8 if axis == 0 else None)
+    dev = dict(kw)
+    dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+    dev["launch_params"] = {"kernel": "twopass"}
+    want = fdtdz_jax.fdtdz(**dev).cpu().numpy()
+    got = fdtdz_decomposed(**kw).cpu().numpy()   # world = 1: the slab wraps onto itself
+    np.testing.assert_array_equal(got, want)
+
+
+def _gpu_worker(rank, world, port, out_path):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  from pjz_b200._decomp import fdtdz_decomposed
+  from tests.problems import random_problem
+  kw = random_problem(domain=(40, 24, 32), axis=0, pml=(4, 6), tt=40, seed=77,
+                      output_steps=(20, 40, 6), src_pos=20)
+  out = fdtdz_decomposed(**kw).cpu().numpy()
+  if rank == 0:
+    np.save(out_path, out)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_decomposition_is_bit_exact(built, tmp_path):
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs")
+  from oracle import fdtd_c
+  from tests.problems import random_problem
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "dd.npy")
+  mp.spawn(_gpu_worker, args=(2, port, out), nprocs=2, join=True)
+  kw = random_problem(domain=(40, 24, 32), axis=0, pml=(4, 6), tt=40, seed=77,
+                      output_steps=(20, 40, 6), src_pos=20)
+  np.testing.assert_array_equal(np.load(out), fdtd_c.fdtdz(**kw))
