@@ -193,6 +193,70 @@ def _exchange(send, recv, to_rank, from_rank, group, world):
     w.wait()
 
 
+class DecomposedRun:
+  """One x-decomposed engine call, split into set-up (``__init__``: slab inputs, session,
+  coefficient preparation) and the time loop (``run``), so benchmarks can time the loop alone."""
+
+  def __init__(self, kw, group=None, make_slab=None, device=None):
+    self.kw, self.group = kw, group
+    self.world, self.rank = 1, 0
+    if dist.is_available() and dist.is_initialized():
+      self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    loc, self.nloc, self.crop = local_problem(kw, self.rank, self.world)
+    if make_slab is None:
+      if not torch.cuda.is_available():
+        raise RuntimeError("fdtdz_decomposed needs a CUDA device (no CPU fallback)")
+      dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+      self.slab = CudaSlab(loc, dev)
+    else:
+      self.slab = make_slab(loc)
+    self.tt = _np(kw["source_waveform"]).shape[0]
+
+  def _peer(self, r):
+    r %= self.world
+    if self.group is not None and self.world > 1:
+      return dist.get_global_rank(self.group, r)
+    return r
+
+  def run(self):
+    slab, nloc, group, world = self.slab, self.nloc, self.group, self.world
+    right, left = self._peer(self.rank + 1), self._peer(self.rank - 1)
+    E, H = slab.E, slab.H                                    # (3, nloc+2, Y, Zp)
+    face = torch.empty_like(H[:, 0].contiguous())            # packed (3, Y, Zp) receive buffer
+    for n in range(self.tt):
+      slab.step_h()
+      # my last owned H plane -> right neighbour's low ghost; my low ghost <- left neighbour
+      _exchange(H[:, nloc].contiguous(), face, right, left, group, world)
+      H[:, 0].copy_(face)
+      slab.step_e(n)
+      # my first owned E plane -> left neighbour's high ghost; my high ghost <- right neighbour
+      _exchange(E[:, 1].contiguous(), face, left, right, group, world)
+      E[:, nloc + 1].copy_(face)
+
+  def local_snapshots(self):
+    """(x_lo, x_hi, snapshots[:, :, x_lo:x_hi]) of this rank, in output coordinates."""
+    snaps = self.slab.snapshots()                            # (n_out, 3, nloc+2, yy, zz)
+    if not isinstance(snaps, torch.Tensor):
+      snaps = torch.from_numpy(np.ascontiguousarray(snaps))
+    if self.crop is None:
+      return 0, 0, snaps[:, :, :0]
+    return self.crop[2], self.crop[3], snaps[:, :, self.crop[0]:self.crop[1]]
+
+  def gathered_snapshots(self):
+    lo, hi, snaps = self.local_snapshots()
+    shape = tuple(self.kw["epsilon"].shape)
+    full = torch.zeros((snaps.shape[0], 3) + shape[1:], dtype=torch.float32, device=snaps.device)
+    if hi > lo:
+      full[:, :, lo:hi] = snaps
+    if self.world > 1:
+      dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)   # disjoint slabs: sum == concat
+    return full
+
+  def close(self):
+    if hasattr(self.slab, "close"):
+      self.slab.close()
+
+
 def fdtdz_decomposed(epsilon, dt, source_field, source_waveform, source_position,
                      absorption_mask, pml_kappa, pml_sigma, pml_alpha, pml_widths,
                      output_steps, use_reduced_precision, launch_params=None, offset=(0, 0, 0),
@@ -210,48 +274,9 @@ def fdtdz_decomposed(epsilon, dt, source_field, source_waveform, source_position
             pml_widths=pml_widths, output_steps=output_steps,
             use_reduced_precision=use_reduced_precision, launch_params=launch_params,
             offset=offset)
-  world, rank = 1, 0
-  if dist.is_available() and dist.is_initialized():
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-  loc, nloc, crop = local_problem(kw, rank, world)
-  if make_slab is None:
-    if not torch.cuda.is_available():
-      raise RuntimeError("fdtdz_decomposed needs a CUDA device (no CPU fallback)")
-    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    slab = CudaSlab(loc, dev)
-  else:
-    slab = make_slab(loc)
-  tt = _np(source_waveform).shape[0]
-
-  def peer(r):
-    r %= world
-    return dist.get_global_rank(group, r) if (group is not None and world > 1) else r
-  right, left = peer(rank + 1), peer(rank - 1)
-  E, H = slab.E, slab.H                                      # (3, nloc+2, Y, Zp)
-  face = torch.empty_like(H[:, 0].contiguous())              # packed (3, Y, Zp) receive buffer
-  for n in range(tt):
-    slab.step_h()
-    # my last owned H plane -> right neighbour's low ghost; my low ghost <- left neighbour
-    _exchange(H[:, nloc].contiguous(), face, right, left, group, world)
-    H[:, 0].copy_(face)
-    slab.step_e(n)
-    # my first owned E plane -> left neighbour's high ghost; my high ghost <- right neighbour
-    _exchange(E[:, 1].contiguous(), face, left, right, group, world)
-    E[:, nloc + 1].copy_(face)
-  snaps = slab.snapshots()                                   # (n_out, 3, nloc+2, yy, zz)
-  if not isinstance(snaps, torch.Tensor):
-    snaps = torch.from_numpy(np.ascontiguousarray(snaps))
-  eps_shape = _np(epsilon).shape if not isinstance(epsilon, torch.Tensor) else tuple(epsilon.shape)
-  n_out = snaps.shape[0]
-  if not gather:
-    if crop is None:
-      return 0, 0, snaps[:, :, :0]
-    return crop[2], crop[3], snaps[:, :, crop[0]:crop[1]]
-  full = torch.zeros((n_out, 3) + tuple(eps_shape[1:]), dtype=torch.float32, device=snaps.device)
-  if crop is not None:
-    full[:, :, crop[2]:crop[3]] = snaps[:, :, crop[0]:crop[1]]
-  if world > 1:
-    dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)  # slabs are disjoint: sum == concat
-  if hasattr(slab, "close"):
-    slab.close()
-  return full
+  run = DecomposedRun(kw, group=group, make_slab=make_slab, device=device)
+  run.run()
+  out = run.gathered_snapshots() if gather else run.local_snapshots()
+  if gather:
+    run.close()
+  return out
