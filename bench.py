@@ -48,6 +48,7 @@ def parse():
   ap.add_argument("--stages", type=int, default=0)
   ap.add_argument("--threads", type=int, default=0)
   ap.add_argument("--prefetch", type=int, default=0)
+  ap.add_argument("--cols", type=int, default=0)
   ap.add_argument("--reduced", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
@@ -76,7 +77,7 @@ def make_workload(args, rank):
     name += f" (tt overridden to {args.tt})"
   lp = {"kernel": args.kernel}
   for k, v in (("tile_y", args.tile_y), ("stages", args.stages), ("threads", args.threads),
-               ("prefetch", args.prefetch)):
+               ("prefetch", args.prefetch), ("cols", args.cols)):
     if v:
       lp[k] = v
   params = params._replace(launch_params=lp)

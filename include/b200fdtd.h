@@ -99,7 +99,8 @@ typedef struct b200fdtd_desc {
   int32_t stages;               /* systolic: time steps in flight along the x sweep         */
   int32_t threads;              /* CTA size override                                        */
   int32_t prefetch;             /* systolic_async: planes of prefetch distance (1..3)       */
-  int32_t reserved[3];
+  int32_t cols;                 /* systolic_async: columns per compute thread (1 | 2)       */
+  int32_t reserved[2];
 } b200fdtd_desc;
 
 /* ABI version of the loaded library. */

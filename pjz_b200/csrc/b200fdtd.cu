@@ -72,6 +72,7 @@ static int validate(const b200fdtd_desc* d) {
                 d->out_stop, d->out_step, d->tt);
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
   if (d->kernel < 0 || d->kernel > 4) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  if (d->cols < 0 || d->cols > 2) return fail(B200FDTD_EINVAL, "cols must be 0, 1 or 2");
   return B200FDTD_OK;
 }
 
@@ -125,10 +126,11 @@ static int device_props(int* sms, int* l2_bytes) {
 template <typename T>
 static bool configure_async(const Geom& g, const b200fdtd_desc* d, int depth, int sms, int l2,
                             SystolicCfg* cfg, std::string* why) {
+  const int K = d->cols == 1 ? 1 : 2;            // columns per compute thread (0 = default 2)
   switch (depth) {
-    case 1: return systolic2_configure_d<T, 1>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
-    case 2: return systolic2_configure_d<T, 2>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
-    case 3: return systolic2_configure_d<T, 3>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
+    case 1: return systolic2_configure_d<T, 1>(g, d->tile_y, d->stages, d->threads, sms, l2, K, cfg, why);
+    case 2: return systolic2_configure_d<T, 2>(g, d->tile_y, d->stages, d->threads, sms, l2, K, cfg, why);
+    case 3: return systolic2_configure_d<T, 3>(g, d->tile_y, d->stages, d->threads, sms, l2, K, cfg, why);
   }
   *why = "prefetch must be 1, 2 or 3";
   return false;

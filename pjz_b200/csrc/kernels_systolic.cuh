@@ -46,6 +46,7 @@ struct SystolicCfg {
   int trap_on_timeout;
   int pf_ahead;          // systolic_async: planes of L2 prefetch beyond the staging ring
   int svc_sleep_ns;      // systolic_async: back-off of the poller / publisher warps
+  int cols;              // systolic_async: adjacent columns per compute thread (1 or 2)
   long long l2_window_bytes;
 };
 

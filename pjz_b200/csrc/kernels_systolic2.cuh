@@ -107,8 +107,10 @@ struct Sys2Ctl {
   unsigned exit_;     // compute warps are finished
 };
 
-template <typename T, int D>
-__global__ void __launch_bounds__(kSys2MaxCompute + kSys2Service)
+// K = adjacent columns per compute thread: 2 (7 compute warps, ~250 registers, fewest
+// instructions per cell) or 1 (14 compute warps, <= 128 registers, twice the warps to hide latency).
+template <typename T, int D, int K>
+__global__ void __launch_bounds__(K == 2 ? kSys2MaxCompute + kSys2Service : 2 * kSys2MaxCompute + kSys2Service)
 systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sync) {
   constexpr int VW = VecTraits<T>::VW;
   constexpr int NE = D + 2, NH = D + 1;
@@ -129,7 +131,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   float4* const sH = sE + (size_t)NE * eslot;                // [NH][3][ring]
   float4* const sB = sH + (size_t)NH * eslot;                // [NH][3][ring]
   float4* const sX = sB + (size_t)NH * eslot;                // [2 | 5][NTc] new H at pair boundaries
-  float4* const sP = sX + (size_t)(cfg.need_zfix ? 5 : 2) * NTc;   // [NH][4][npsi]
+  float4* const sP = sX + (size_t)(cfg.need_zfix ? 1 + 2 * K : 2) * NTc;   // [NH][4][npsi]
   float4* const sT = sP + (size_t)NH * pslot;                // [6][Zp/4] CPML tables
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
@@ -211,12 +213,12 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const int Zq = g.Zq, X = g.X;
   const int cp = tid / Zq, q = tid - cp * Zq;
   const int ncols = Yt + 2;
-  int f[2], yk[2];
-  bool act[2], doH[2], own[2];
-  unsigned coff[2];                                // element offset inside a plane (< 2^31)
+  int f[K], yk[K];
+  bool act[K], doH[K], own[K];
+  unsigned coff[K];                                // element offset inside a plane (< 2^31)
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int c = 2 * cp + k;
+  for (int k = 0; k < K; ++k) {
+    const int c = K * cp + k;
     act[k] = c < ncols;
     doH[k] = c <= Yt;
     own[k] = c >= 1 && c <= Yt;
@@ -228,9 +230,9 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const bool has_psi = slot >= 0;
   const size_t pplane = (size_t)g.Y * g.npg * VW;
   const size_t gP = (size_t)g.P;
-  unsigned ppoff[2];                               // psi offset of the item inside a plane (< 2^31)
+  unsigned ppoff[K];                               // psi offset of the item inside a plane (< 2^31)
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < K; ++k)
     ppoff[k] = (unsigned)((yk[k] * g.npg + (has_psi ? slot : 0)) * VW);
   const bool fix_up = cfg.need_zfix && lane == 31 && q + 1 < Zq;
   const bool fix_dn = cfg.need_zfix && lane == 0 && q > 0;
@@ -240,9 +242,9 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
   const float4* const tq = sT + q * PV;            // CPML table w of this z-group: tq[w*tstride + v]
   // plane source: cheap pre-test so that add_source() is off the common path
   const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : g.Y);
-  bool src_thr[2];
+  bool src_thr[K];
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < K; ++k)
     src_thr[k] = g.src_axis == 1 ? (yk[k] == sp0 || yk[k] == sp1)
                                  : (g.src_axis == 2 && q == g.src_pos / VW);
   bool ok = true;
@@ -312,7 +314,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       float4* const hb = sH + sh * eslot;
       float4* const bb = sB + sh * eslot;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < K; ++k) {
         if (act[k]) {
         const size_t offP = pP + coff[k], offN = pN + coff[k];
         cp_async16(eb + f[k], p.Es[rb][0] + offN);
@@ -333,7 +335,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
             cp_async16(bb + 2 * ring + f[k], p.B[2] + offP);
           }
           if (has_psi) {
-            float4* ps = sP + sh * pslot + ((2 * cp + k) * g.npg + slot) * PV;
+            float4* ps = sP + sh * pslot + ((K * cp + k) * g.npg + slot) * PV;
             const size_t po = (size_t)P * pplane + ppoff[k];
 #pragma unroll
             for (int v = 0; v < PV; ++v) {
@@ -364,12 +366,14 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       PL = PLn;
     }
 
-    float hyp[2][VW], hzp[2][VW];                  // H^{n+1/2}[P-1] of the thread's own cells
+    float hyp[K][VW], hzp[K][VW];                  // H^{n+1/2}[P-1] of the thread's own cells
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int v = 0; v < VW; ++v) { hyp[k][v] = 0.f; hzp[k][v] = 0.f; }
-    float an[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};   // absorber rows of the NEXT plane
+    float an[K][3];                                // absorber rows of the NEXT plane
+#pragma unroll
+    for (int k = 0; k < K; ++k) { an[k][0] = 0.f; an[k][1] = 0.f; an[k][2] = 0.f; }
     int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
     int se = 0, sh = 0;                            // ring slots of E[P] and H/B/psi[P]
 
@@ -399,9 +403,9 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         PL = PLn;
       }
 
-      float a[2][3];
+      float a[K][3];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < K; ++k) {
         a[k][0] = an[k][0]; a[k][1] = an[k][1]; a[k][2] = an[k][2];
         if (own[k] && i < X) {
           const size_t xy = (size_t)Pn * g.Y + yk[k];
@@ -412,28 +416,28 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       const float4* const eN = sE + sen * eslot;   // E^n[P+1]
       const float4* const hO = sH + sh * eslot;    // H^{n-1/2}[P]
       const float4* const bC = sB + sh * eslot;    // B[P]
-      const float4* const pS = sP + sh * pslot + (2 * cp * g.npg + (has_psi ? slot : 0)) * PV;
+      const float4* const pS = sP + sh * pslot + (K * cp * g.npg + (has_psi ? slot : 0)) * PV;
       const int pstep = g.npg * PV;                // item 1's psi vectors follow item 0's column
 
-      float ex[2][VW], ey[2][VW], ez[2][VW], hx[2][VW], hy[2][VW], hz[2][VW];
+      float ex[K][VW], ey[K][VW], ez[K][VW], hx[K][VW], hy[K][VW], hz[K][VW];
       {
         float ah[VW], bh[VW], ikh[VW];
         load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < K; ++k) {
           unpack(eC[f[k]], ex[k], T()); unpack(eC[ring + f[k]], ey[k], T());
           unpack(eC[2 * ring + f[k]], ez[k], T());
           unpack(hO[f[k]], hx[k], T()); unpack(hO[ring + f[k]], hy[k], T());
           unpack(hO[2 * ring + f[k]], hz[k], T());
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < K; ++k) {
           float ez_yp[VW], ex_yp[VW], ey_xp[VW], ez_xp[VW], psx[VW], psy[VW];
-          if (k == 0) {
+          if (k + 1 < K) {                         // next column is this thread's own
 #pragma unroll
-            for (int v = 0; v < VW; ++v) { ez_yp[v] = ez[1][v]; ex_yp[v] = ex[1][v]; }
+            for (int v = 0; v < VW; ++v) { ez_yp[v] = ez[(k + 1) % K][v]; ex_yp[v] = ex[(k + 1) % K][v]; }
           } else {
-            const int nb = doH[1] ? f[1] + Zq : f[1];
+            const int nb = doH[K - 1] ? f[K - 1] + Zq : f[K - 1];
             unpack(eC[2 * ring + nb], ez_yp, T()); unpack(eC[nb], ex_yp, T());
           }
           unpack(eN[ring + f[k]], ey_xp, T()); unpack(eN[2 * ring + f[k]], ez_xp, T());
@@ -466,35 +470,37 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
       }
 
       // pair boundary: the odd column's new H is the y-1 neighbour of the next thread's even one
-      const float4 hx1v = pack(hx[1], T()), hz1v = pack(hz[1], T());
-      sX[tid] = hz1v;
-      sX[NTc + tid] = hx1v;
-      if (cfg.need_zfix) {                         // cross-warp z-1 neighbours need Hx, Hy of both
-        sX[2 * NTc + tid] = pack(hy[1], T());
-        sX[3 * NTc + tid] = pack(hx[0], T());
-        sX[4 * NTc + tid] = pack(hy[0], T());
+      sX[tid] = pack(hz[K - 1], T());
+      sX[NTc + tid] = pack(hx[K - 1], T());
+      if (cfg.need_zfix) {                         // cross-warp z-1 neighbours need Hx, Hy of all
+        sX[2 * NTc + tid] = pack(hy[K - 1], T());
+#pragma unroll
+        for (int k = 0; k + 1 < K; ++k) {
+          sX[(3 + 2 * k) * NTc + tid] = pack(hx[k], T());
+          sX[(4 + 2 * k) * NTc + tid] = pack(hy[k], T());
+        }
       }
       bar_compute(NTc);                            // B_i
       if (real) {
         float ae[VW], be[VW], ike[VW];
         load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < K; ++k) {
           float hx_bot = __shfl_up_sync(0xffffffffu, hx[k][VW - 1], 1);
           float hy_bot = __shfl_up_sync(0xffffffffu, hy[k][VW - 1], 1);
           if (fix_dn) {
             float tmp[VW];
-            unpack(sX[(k == 1 ? NTc : 3 * NTc) + tid - 1], tmp, T()); hx_bot = tmp[VW - 1];
-            unpack(sX[(k == 1 ? 2 * NTc : 4 * NTc) + tid - 1], tmp, T()); hy_bot = tmp[VW - 1];
+            unpack(sX[(k == K - 1 ? 1 : 3 + 2 * k) * NTc + tid - 1], tmp, T()); hx_bot = tmp[VW - 1];
+            unpack(sX[(k == K - 1 ? 2 : 4 + 2 * k) * NTc + tid - 1], tmp, T()); hy_bot = tmp[VW - 1];
           }
           if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
           if (own[k]) {
             const size_t offP = pP + coff[k];
             float hz_ym[VW], hx_ym[VW], qsx[VW], qsy[VW], b0[VW], b1[VW], b2[VW];
-            if (k == 1) {
+            if (k > 0) {                           // previous column is this thread's own
 #pragma unroll
-              for (int v = 0; v < VW; ++v) { hz_ym[v] = hz[0][v]; hx_ym[v] = hx[0][v]; }
-            } else {                               // even column >= 2: previous thread's odd column
+              for (int v = 0; v < VW; ++v) { hz_ym[v] = hz[(k + K - 1) % K][v]; hx_ym[v] = hx[(k + K - 1) % K][v]; }
+            } else {                               // previous thread's last column
               unpack(sX[tid - Zq], hz_ym, T());
               unpack(sX[NTc + tid - Zq], hx_ym, T());
             }
@@ -535,7 +541,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
         }
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int v = 0; v < VW; ++v) { hyp[k][v] = hy[k][v]; hzp[k][v] = hz[k][v]; }
       P = Pn;
@@ -552,43 +558,44 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
 }
 
 // compute threads of a CTA that owns `tile_y` columns: one thread per z-vector of a column pair
-inline int systolic2_compute_threads(const Geom& g, int tile_y) {
-  return ((tile_y + 3) / 2 * g.Zq + 31) / 32 * 32;
+inline int systolic2_compute_threads(const Geom& g, int tile_y, int K = 2) {
+  return ((tile_y + 2 + K - 1) / K * g.Zq + 31) / 32 * 32;
 }
 
 template <typename T, int D>
-size_t systolic2_smem_bytes(const Geom& g, int tile_y) {
+size_t systolic2_smem_bytes(const Geom& g, int tile_y, int K = 2) {
   constexpr int PV = VecTraits<T>::VW / 4;
   const size_t npsi = (size_t)(tile_y + 2) * g.npg * PV;
   const size_t ring = (size_t)(tile_y + 2) * g.Zq;
   const bool zfix = 32 % g.Zq != 0;
   return sizeof(float4) * ((size_t)((D + 2) * 3 + 2 * (D + 1) * 3) * ring +
-                           (size_t)(zfix ? 5 : 2) * systolic2_compute_threads(g, tile_y) +
+                           (size_t)(zfix ? 1 + 2 * K : 2) * systolic2_compute_threads(g, tile_y, K) +
                            (size_t)(D + 1) * 4 * npsi + 6 * (size_t)g.Zp / 4);
 }
 
 template <typename T, int D>
 bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int threads_req, int sms,
-                           int l2_bytes, SystolicCfg* cfg, std::string* why) {
-  const int max_threads = threads_req > 0 ? (threads_req < kSys2MaxCompute ? threads_req : kSys2MaxCompute)
-                                          : kSys2MaxCompute;
+                           int l2_bytes, int K, SystolicCfg* cfg, std::string* why) {
+  const int cap = K == 2 ? kSys2MaxCompute : 2 * kSys2MaxCompute;
+  const int max_threads = threads_req > 0 ? (threads_req < cap ? threads_req : cap) : cap;
   if (g.Zq * 2 > max_threads) { *why = "z extent too large for one CTA"; return false; }
-  int max_tile = 2 * (max_threads / g.Zq) - 2;
+  int max_tile = K * (max_threads / g.Zq) - 2;
   // largest tile whose staging ring fits in shared memory
-  while (max_tile >= 1 && (systolic2_compute_threads(g, max_tile) > max_threads ||
-                           systolic2_smem_bytes<T, D>(g, max_tile) + 64 > 227 * 1024))
+  while (max_tile >= 1 && (systolic2_compute_threads(g, max_tile, K) > max_threads ||
+                           systolic2_smem_bytes<T, D>(g, max_tile, K) + 64 > 227 * 1024))
     --max_tile;
   if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
   if (max_tile > g.Y) max_tile = g.Y;
   const int ntiles = (g.Y + max_tile - 1) / max_tile;
   const int widest = (g.Y + ntiles - 1) / ntiles;
-  const int compute = systolic2_compute_threads(g, widest);
+  const int compute = systolic2_compute_threads(g, widest, K);
   cfg->tile_y = widest;
   cfg->ntiles = ntiles;
+  cfg->cols = K;
   cfg->threads = compute + kSys2Service;
   cfg->need_zfix = (32 % g.Zq != 0);
-  cfg->smem_bytes = (int)systolic2_smem_bytes<T, D>(g, widest);
+  cfg->smem_bytes = (int)systolic2_smem_bytes<T, D>(g, widest, K);
   // >= 2D+4 is needed for deadlock freedom (a throttled stage has published i-2 indices while its
   // successor needs i'+D+2 of them to advance); the rest is slack for the
   // polling/publishing latency.
@@ -603,10 +610,11 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
   int occ = 0;
-  if (cudaFuncSetAttribute(systolic2_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           cfg->smem_bytes) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, systolic2_kernel<T, D>, cfg->threads,
-                                                    cfg->smem_bytes) != cudaSuccess || occ < 1) {
+  const void* fn = K == 2 ? (const void*)systolic2_kernel<T, D, 2> : (const void*)systolic2_kernel<T, D, 1>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
+          cudaSuccess || occ < 1) {
     cudaGetLastError();
     *why = "kernel does not fit on an SM";
     return false;
@@ -630,14 +638,16 @@ bool systolic2_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
 template <typename T, int D>
 int systolic2_launch_d(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
                        cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(systolic2_kernel<T, D>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.smem_bytes);
+  const void* fn = cfg.cols == 2 ? (const void*)systolic2_kernel<T, D, 2>
+                                 : (const void*)systolic2_kernel<T, D, 1>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   Geom gg = g;
   Ptrs<T> pp = p;
   SystolicCfg cc = cfg;
   void* args[] = {&gg, &pp, &cc, &sync};
-  e = cudaLaunchCooperativeKernel((const void*)systolic2_kernel<T, D>,
+  e = cudaLaunchCooperativeKernel(fn,
                                   dim3(cfg.stages * cfg.ntiles), dim3(cfg.threads), args,
                                   cfg.smem_bytes, st);
   if (e != cudaSuccess) return (int)e;

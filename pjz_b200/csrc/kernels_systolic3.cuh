@@ -577,6 +577,7 @@ bool systolic3_configure_d(const Geom& g, int tile_y_req, int stages_req, int th
   cfg->max_lead = 2 * D + 8;
   cfg->pf_ahead = 6;
   cfg->svc_sleep_ns = 0;
+  cfg->cols = 2;
   if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
   if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
   if (cfg->max_lead < 2 * D + 4) cfg->max_lead = 2 * D + 4;

@@ -41,8 +41,8 @@ class Desc(ctypes.Structure):
                   "out_stop", "out_step", "use_reduced_precision")] +
               [("dt", ctypes.c_float)] +
               [(n, ctypes.c_int32) for n in ("kernel", "tile_y", "stages", "threads",
-                                             "prefetch")] +
-              [("reserved", ctypes.c_int32 * 3)])
+                                             "prefetch", "cols")] +
+              [("reserved", ctypes.c_int32 * 2)])
 
 
 _lib = None
@@ -131,15 +131,15 @@ def make_desc(epsilon, dt, source_field, source_waveform, source_position, absor
   if not isinstance(lp, dict):
     raise ValueError("launch_params must be None or a dict (kernel, tile_y, stages, threads, "
                      "prefetch)")
-  unknown = set(lp) - {"kernel", "tile_y", "stages", "threads", "prefetch"}
+  unknown = set(lp) - {"kernel", "tile_y", "stages", "threads", "prefetch", "cols"}
   if unknown:
     raise ValueError(f"unknown launch_params keys {sorted(unknown)}")
   k = lp.get("kernel", "auto")
   if k not in _KERNELS:
     raise ValueError(f"launch_params['kernel'] must be one of {sorted(_KERNELS)}, got {k!r}")
   d.kernel = _KERNELS[k]
-  d.tile_y, d.stages, d.threads, d.prefetch = (
-      int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads", "prefetch"))
+  d.tile_y, d.stages, d.threads, d.prefetch, d.cols = (
+      int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads", "prefetch", "cols"))
   rc = lib().b200fdtd_validate(ctypes.byref(d))
   if rc != 0:
     raise ValueError(_last_error())

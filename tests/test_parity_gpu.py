@@ -83,14 +83,26 @@ def test_ragged_and_degenerate_domains(domain, pml, kernel):
     np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
 
 
+@pytest.mark.parametrize("cols", [1, 2])
 @pytest.mark.parametrize("prefetch", [1, 2, 3])
 @pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (6, 3), (4, 40)])
-def test_systolic_async_tilings(tile_y, stages, prefetch):
+def test_systolic_async_tilings(tile_y, stages, prefetch, cols):
   kw = random_problem(domain=(11, 23, 16), axis=1, pml=(4, 4), tt=45, seed=13,
                       output_steps=(20, 45, 6))
   want = fdtd_c.fdtdz(**kw)
-  out = run_gpu(kw, kernel="systolic_async", tile_y=tile_y, stages=stages, prefetch=prefetch)
+  out = run_gpu(kw, kernel="systolic_async", tile_y=tile_y, stages=stages, prefetch=prefetch,
+                cols=cols)
   np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("domain,pml", [((20, 18, 96), (16, 16)), ((10, 12, 128), (16, 16)),
+                                        ((9, 7, 13), (3, 5)), ((5, 6, 256), (10, 12))])
+def test_systolic_async_one_column_per_thread(domain, pml):
+  for axis in (0, 2):
+    kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
+                        seed=7, output_steps=(5, 14, 4), absorb_pad=2)
+    np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_async", cols=1),
+                                  fdtd_c.fdtdz(**kw))
 
 
 @pytest.mark.parametrize("prefetch", [1, 2])
