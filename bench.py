@@ -43,7 +43,8 @@ def parse():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="bend", choices=["bend", "waveguide", "demux", "coupler"])
   ap.add_argument("--tt", type=int, default=0, help="override the number of FDTD steps")
-  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic", "systolic_async", "systolic_tma"])
+  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic", "systolic_async", "systolic_tma",
+                                                       "systolic_lean"])
   ap.add_argument("--tile-y", type=int, default=0)
   ap.add_argument("--stages", type=int, default=0)
   ap.add_argument("--threads", type=int, default=0)

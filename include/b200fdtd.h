@@ -74,8 +74,10 @@ enum {
                                    stages, operands staged through registers               */
   B200FDTD_KERNEL_SYSTOLIC_ASYNC = 3, /* same protocol; operands staged through a cp.async
                                    shared-memory ring, service warp for the protocol       */
-  B200FDTD_KERNEL_SYSTOLIC_TMA = 4 /* same protocol; operands staged by TMA bulk copies
+  B200FDTD_KERNEL_SYSTOLIC_TMA = 4, /* same protocol; operands staged by TMA bulk copies
                                    (cp.async.bulk + mbarrier) issued by the service warp    */
+  B200FDTD_KERNEL_SYSTOLIC_LEAN = 5 /* same protocol; one warp per column pair, no CTA barrier in
+                                   the plane loop (fp32, z-column of exactly 32 vectors)     */
 };
 
 /* Static description of one engine call (everything that is a python scalar/tuple at

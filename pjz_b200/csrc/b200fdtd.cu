@@ -20,6 +20,7 @@
 #include "kernels_systolic.cuh"
 #include "kernels_systolic2.cuh"
 #include "kernels_systolic3.cuh"
+#include "kernels_lean.cuh"
 #include "kernels_twopass.cuh"
 
 namespace b200 {
@@ -71,7 +72,7 @@ static int validate(const b200fdtd_desc* d) {
     return fail(B200FDTD_EINVAL, "output_steps (%d,%d,%d) outside [0,tt=%d)", d->out_start,
                 d->out_stop, d->out_step, d->tt);
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
-  if (d->kernel < 0 || d->kernel > 4) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  if (d->kernel < 0 || d->kernel > 5) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
   if (d->cols < 0 || d->cols > 2) return fail(B200FDTD_EINVAL, "cols must be 0, 1 or 2");
   return B200FDTD_OK;
 }
@@ -112,7 +113,7 @@ struct Plan {
 
 static bool is_systolic(int k) {
   return k == B200FDTD_KERNEL_SYSTOLIC || k == B200FDTD_KERNEL_SYSTOLIC_ASYNC ||
-         k == B200FDTD_KERNEL_SYSTOLIC_TMA;
+         k == B200FDTD_KERNEL_SYSTOLIC_TMA || k == B200FDTD_KERNEL_SYSTOLIC_LEAN;
 }
 
 static int device_props(int* sms, int* l2_bytes) {
@@ -158,6 +159,12 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   int rc = device_props(&sms, &l2);
   if (rc) return rc;
   std::string why;
+  if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
+    if (!lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why))
+      return fail(B200FDTD_EUNSUPPORTED, "systolic_lean kernel unavailable: %s", why.c_str());
+    plan->depth = 1;
+    return B200FDTD_OK;
+  }
   if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_TMA) {
     const int depth = d->prefetch > 0 ? d->prefetch : 1;
     if (!configure_tma<T>(g, d, depth, sms, l2, &plan->sys, &why))
@@ -197,7 +204,7 @@ struct Workspace {
   size_t psi;      // psiH[2], psiE[2]  (zeroed)
   size_t sync;     // progress counters + status (zeroed)
   size_t zero_end; // end of the zero-initialised prefix
-  size_t B, A, S, tab;
+  size_t B, A, A4, S, tab;
   size_t total;
 };
 
@@ -213,6 +220,7 @@ static Workspace carve(const Geom& g, bool reduced, bool systolic, const Systoli
   w.zero_end = o;
   w.B = o;       o = align_up(o + 3 * (size_t)g.N * el, 256);
   w.A = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
+  w.A4 = o;      o = align_up(o + 4 * (size_t)g.X * g.Y * sizeof(float), 256);
   w.S = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
   w.tab = o;     o = align_up(o + 6 * (size_t)g.Zp * sizeof(float), 256);
   w.total = o;
@@ -249,12 +257,16 @@ __global__ void prep_tables_kernel(Geom g, const float* __restrict__ kappa,
 }
 
 __global__ void prep_absorber_kernel(Geom g, const float* __restrict__ mask,
-                                     float* __restrict__ A, float* __restrict__ S) {
-  const size_t n = 3 * (size_t)g.X * g.Y;
+                                     float* __restrict__ A, float* __restrict__ A4,
+                                     float* __restrict__ S) {
+  const size_t XY = (size_t)g.X * g.Y, n = 3 * XY;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     const double s = mask[i], h = (double)g.dt / 2;
-    A[i] = (float)((1 - s * h) / (1 + s * h));
+    const float a = (float)((1 - s * h) / (1 + s * h));
+    A[i] = a;
+    A4[4 * (i % XY) + i / XY] = a;
+    if (i < XY) A4[4 * i + 3] = 0.f;
     S[i] = (float)(1 / (1 + s * h));
   }
 }
@@ -308,6 +320,7 @@ static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace&
     p.B[c] = B + (size_t)c * g.N;
   }
   p.A = reinterpret_cast<float*>(ws + w.A);
+  p.A4 = reinterpret_cast<float*>(ws + w.A4);
   p.tab = reinterpret_cast<float*>(ws + w.tab);
   p.psiH[0] = psi; p.psiH[1] = psi + psi_n; p.psiE[0] = psi + 2 * psi_n; p.psiE[1] = psi + 3 * psi_n;
   p.psiH2[0] = psi + 4 * psi_n; p.psiH2[1] = psi + 5 * psi_n;   // carved only for the systolic kernel
@@ -328,7 +341,8 @@ static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace&
       static_cast<const float*>(in[B200FDTD_IN_PML_ALPHA]), d->pml_lo, d->pml_hi,
       const_cast<float*>(p.tab));
   prep_absorber_kernel<<<256, 256, 0, st>>>(
-      g, static_cast<const float*>(in[B200FDTD_IN_ABSORPTION_MASK]), const_cast<float*>(p.A), S);
+      g, static_cast<const float*>(in[B200FDTD_IN_ABSORPTION_MASK]), const_cast<float*>(p.A),
+      const_cast<float*>(p.A4), S);
   prep_b_kernel<T><<<148 * 8, 256, 0, st>>>(
       g, static_cast<const float*>(in[B200FDTD_IN_EPSILON]), S, B);
   CUDA_TRY(cudaGetLastError());
@@ -346,6 +360,10 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
     unsigned* sync = reinterpret_cast<unsigned*>(ws + w.sync);
     int rc;
     if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
+    else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
+      if constexpr (sizeof(T) == 4) rc = lean_launch(g, p, plan.sys, sync, st);
+      else rc = (int)cudaErrorInvalidValue;
+    }
     else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_TMA)
       rc = plan.depth == 2 ? systolic3_launch_d<T, 2>(g, p, plan.sys, sync, st)
                            : systolic3_launch_d<T, 1>(g, p, plan.sys, sync, st);

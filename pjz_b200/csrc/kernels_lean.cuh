@@ -1,0 +1,601 @@
+// Systolic kernel, warp-autonomous generation ("systolic_lean"): the same stage/tile
+// decomposition, ping-pong buffers and inter-CTA progress protocol as kernels_systolic.cuh and
+// kernels_systolic2.cuh (read those headers first), specialised for the flagship geometry
+// -- fp32 storage with a z-column of exactly 32 16-byte vectors (125 <= Z <= 128) -- so that
+// ONE WARP = ONE PAIR OF ADJACENT y-COLUMNS and the plane loop contains no CTA-wide barrier.
+//
+//  * Lane q of warp w owns z-vector q of the tile-local columns 2w and 2w+1 (column 0 is the
+//    y0-1 halo).  z+-1 neighbours are warp shuffles, the y neighbour inside the pair is the
+//    thread's own registers, x-1 is carried in registers along the sweep.
+//  * Every lane stages ITS OWN operand vectors (E^n[P+1] of its two columns and of the column
+//    after the pair, H^{n-1/2}[P], psiH[P]) with cp.async.cg into a per-warp ring one plane
+//    ahead and is the only reader of what it copied: cp.async.wait_group is all the
+//    synchronisation the ring needs.  B[P], psiE[P] and the absorber row travel the same way
+//    (plain loads issued at the top of the iteration were measured to stall the first
+//    shared-memory read of the H half-step: they end up on the same scoreboard).
+//  * The only data that crosses warps is the freshly formed (Hz, Hx) of the pair's second
+//    column -- the y-1 neighbour of the next warp's first column.  It goes through a 2-deep
+//    per-warp shared-memory slot guarded by two monotonic counters (produced / consumed):
+//    a warp waits for its NEIGHBOUR only, never for the whole CTA.
+//  * Inter-CTA dependencies are checked by each warp against the shared-memory mirror the
+//    service warp maintains (as in systolic_async); every warp reports its own finished sweep
+//    index and the service warp publishes the minimum with st.release.gpu.
+//
+// All loop predicates are warp-uniform, array strides are powers of two, addresses are 32-bit
+// vector indices: about 60 instructions per cell-update instead of ~130 in systolic_async.
+#pragma once
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string>
+
+#include "fdtd_common.cuh"
+#include "kernels_systolic.cuh"
+#include "kernels_systolic2.cuh"
+
+namespace b200 {
+
+constexpr int kLeanMaxWarps = 7;       // compute warps per CTA (255-register budget: 8 warps/SM)
+constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
+constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
+constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
+
+struct LeanCtl {
+  unsigned avail;      // min over the three predecessor counters (raw, cumulative)
+  unsigned next;       // successor stage's counter on this tile
+  unsigned ok;         // 0 once any CTA gave up
+  unsigned front;      // cumulative iteration index warp 0 has reached (L2 prefetch cursor)
+  unsigned exited;     // compute warps that have left the time loop
+  unsigned wdone[kLeanMaxWarps + 1];   // per warp: cumulative finished sweep indices
+  unsigned hcnt[kLeanMaxWarps + 1];    // per warp: iterations whose boundary H is in the slot
+  unsigned rcnt[kLeanMaxWarps + 1];    // per warp: iterations the next warp has consumed
+};
+
+__device__ __forceinline__ float4 lds16(const float4* p) { return *p; }
+
+__device__ __forceinline__ void f4_to_arr(const float4 r, float (&v)[4]) {
+  v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+__device__ __forceinline__ float4 arr_to_f4(const float (&v)[4]) {
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// U = unroll factor of the plane loop (2 removes the loop-carried register moves).
+template <int U>
+__global__ void __launch_bounds__(32 * (kLeanMaxWarps + 1), 1)
+lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync) {
+  constexpr int VW = 4;
+  constexpr int ZQ = 32;
+  extern __shared__ float4 smem[];
+  __shared__ LeanCtl ctl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
+  const int S = cfg.stages, NT = cfg.ntiles;
+  const int t = blockIdx.x % NT, j = blockIdx.x / NT;
+  const int y0 = (int)((long long)t * g.Y / NT);
+  const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
+  const int X = g.X, Y = g.Y;
+  const int psi_row = g.npg;                       // float4 per psi row of a slot
+  const int eslot_f4 = kLeanERows * ZQ;
+  const int hslot_f4 = kLeanHRows * ZQ + 8 * psi_row + 2;   // + 8 psi rows + 2 absorber rows
+  const int warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + kLeanXR * 2 * ZQ;
+  const int NWt = min(NW, (Yt + 2) / 2);           // warps with work on THIS tile (balanced tiles)
+
+  unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
+  unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
+
+  if (tid < (int)(sizeof(LeanCtl) / sizeof(unsigned))) reinterpret_cast<unsigned*>(&ctl)[tid] = 0u;
+  __syncthreads();
+  if (tid == 0) ctl.ok = 1u;
+  __syncthreads();
+
+  // =================================== service warp ==============================================
+  if (w == NW) {
+    const int jp = (j + S - 1) % S, jn = (j + 1) % S;
+    const unsigned* watch = sync + ((size_t)jp * NT + wrapi(t - 1 + (lane < 3 ? lane : 1), NT)) *
+                                       kSysFlagStride;
+    if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
+    if (lane == 4) watch = status;
+    // L2 prefetch duty: lanes 8..16 own one array each (E0..2, H0..2 of the read set, B0..2).
+    const int ylo = max(y0 - 1, 0), yhi = min(y0 + Yt, Y - 1);
+    const unsigned pf_bytes = (unsigned)((yhi - ylo + 1) * g.Zp * (int)sizeof(float));
+    const size_t pf_off = (size_t)ylo * g.Zp;
+    unsigned pf_done = 0;
+    const unsigned sweep_iters = (unsigned)X + 1u;
+    unsigned published = 0;
+    while (true) {
+      const unsigned ex = ld_vol_s(&ctl.exited);
+      unsigned dn = lane < NWt ? ld_vol_s(&ctl.wdone[lane]) : 0xffffffffu;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dn = min(dn, __shfl_xor_sync(0xffffffffu, dn, o));
+      if (dn != published) {
+        if (lane == 0) st_release_u32(my_prog, dn);
+        published = dn;
+      } else if (ex == (unsigned)NW) {
+        break;
+      }
+      unsigned v = 0xffffffffu;
+      if (lane < 5) v = ld_relaxed_gpu_u32(watch);
+      const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
+                     v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
+                     v4 = __shfl_sync(0xffffffffu, v, 4);
+      if (lane == 0) {
+        st_vol_s(&ctl.avail, min(v0, min(v1, v2)));
+        st_vol_s(&ctl.next, v3);
+        if (v4 != 0) st_vol_s(&ctl.ok, 0u);
+      }
+      const unsigned front = ld_vol_s(&ctl.front);
+      const unsigned want = front + 1u + (unsigned)cfg.pf_ahead;
+      if (cfg.pf_ahead > 0 && lane >= 8 && lane < 17) {
+        if (pf_done < front + 1u) pf_done = front + 1u;
+        for (; pf_done < want; ++pf_done) {
+          const unsigned sweep = pf_done / sweep_iters, it = pf_done % sweep_iters;
+          const int n = j + (int)sweep * S;
+          if (n >= g.tt) break;
+          const int rb = n & 1;
+          const int P = wrapi(n % X - 1 + (int)it, X), Pn = wrapi(P + 1, X);
+          const int a = lane - 8;
+          const float* base;
+          int plane;
+          if (a < 3) { base = rb ? p.E2[a] : p.E[a]; plane = Pn; }
+          else if (a < 6) { base = rb ? p.H2[a - 3] : p.H[a - 3]; plane = P; }
+          else { base = p.B[a - 6]; plane = P; }
+          prefetch_l2_bulk(base + (size_t)plane * g.P + pf_off, pf_bytes);
+        }
+      }
+      pf_done = __shfl_sync(0xffffffffu, pf_done, 8);
+      __nanosleep(cfg.svc_sleep_ns);
+    }
+    return;
+  }
+
+  // ================================= compute warps ===============================================
+  if (w >= NWt) {                                  // narrower tile: this warp has no column
+    if (lane == 0) atomicAdd(&ctl.exited, 1u);
+    return;
+  }
+  const int q = lane;
+  const int cA = 2 * w, cB = 2 * w + 1;            // tile-local columns; 0 is the y0-1 halo
+  const bool ownA = cA >= 1;                       // (cA <= Yt by construction of NWt)
+  const bool doHB = cB <= Yt;                      // column B forms H and is owned
+  const int yA = wrapi(y0 - 1 + cA, Y), yB = wrapi(y0 - 1 + cB, Y);
+  const int yC = wrapi(y0 - 1 + (doHB ? cB + 1 : cB), Y);
+  const unsigned PVn = (unsigned)Y * ZQ;           // vectors per x-plane
+  const unsigned tvA = (unsigned)yA * ZQ + q, tvB = (unsigned)yB * ZQ + q, tvC = (unsigned)yC * ZQ + q;
+  const int slot = psi_slot(g, q);
+  const bool has_psi = slot >= 0;
+  const unsigned PPn = (unsigned)Y * g.npg;        // psi vectors per x-plane
+  const unsigned pvA = (unsigned)yA * g.npg + (has_psi ? slot : 0);
+  const unsigned pvB = (unsigned)yB * g.npg + (has_psi ? slot : 0);
+  const bool top = q + 1 == ZQ, bottom = q == 0;
+
+  float4* const wbase = smem + (size_t)w * warp_f4;
+  float4* const hbase = wbase + 3 * eslot_f4;
+  float4* const xmine = hbase + 2 * hslot_f4 + q;                // boundary-H slots this warp writes
+  const float4* const xprev = xmine - warp_f4;                   // ... and those of warp w-1
+
+  // CPML tables of this z-group live in registers for the whole run
+  float ae[VW], be[VW], ike[VW], ah[VW], bh[VW], ikh[VW];
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 0 * g.Zp) + q), ae);
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 1 * g.Zp) + q), be);
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 2 * g.Zp) + q), ike);
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 3 * g.Zp) + q), ah);
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 4 * g.Zp) + q), bh);
+  f4_to_arr(__ldg(reinterpret_cast<const float4*>(p.tab + 5 * g.Zp) + q), ikh);
+
+  // plane source: cheap warp-uniform pre-tests so that add_source() stays off the common path
+  const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : Y);
+  const bool srcA = g.src_axis == 1 ? (yA == sp0 || yA == sp1) : g.src_axis == 2;
+  const bool srcB = g.src_axis == 1 ? (yB == sp0 || yB == sp1) : g.src_axis == 2;
+  const float dt = g.dt;
+  const float4* const A4 = reinterpret_cast<const float4*>(p.A4);
+
+  bool ok = true;
+  unsigned kk = 0;                                 // cumulative iteration count (never reset)
+  unsigned iters_done = 0;
+
+  // Spin (all lanes, warp-uniform verdict) until cond() holds; false = give up.
+  auto spin = [&](auto cond) -> bool {
+    if (__all_sync(0xffffffffu, cond())) return true;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+      if (__all_sync(0xffffffffu, cond())) return true;
+      if (__any_sync(0xffffffffu, ld_vol_s(&ctl.ok) == 0)) return false;
+      __nanosleep(32);                             // leave the issue slots to the other warps
+      if ((++spins & 255u) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 5000000000ull) {
+          if (lane == 0) { atomicCAS(status, 0u, 1u + blockIdx.x); st_vol_s(&ctl.ok, 0u); }
+          return false;
+        }
+      }
+    }
+  };
+
+  for (int n = j; n < g.tt && ok; n += S) {
+    const int m = n / S;
+    const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)X;
+    const unsigned base_mine = (unsigned)m * (unsigned)X;
+    const bool has_prev = n > 0, has_next = n + 1 < g.tt && j + 1 < S;
+    const int rb = n & 1, wb = rb ^ 1;
+    const int cstart = n % X;
+    const int oi = snapshot_index(g, n);
+    const float w0 = __ldg(p.wave + 2 * (size_t)n), w1 = __ldg(p.wave + 2 * (size_t)n + 1);
+    const float4* const rEx = reinterpret_cast<const float4*>(p.Es[rb][0]);
+    const float4* const rEy = reinterpret_cast<const float4*>(p.Es[rb][1]);
+    const float4* const rEz = reinterpret_cast<const float4*>(p.Es[rb][2]);
+    const float4* const rHx = reinterpret_cast<const float4*>(p.Hs[rb][0]);
+    const float4* const rHy = reinterpret_cast<const float4*>(p.Hs[rb][1]);
+    const float4* const rHz = reinterpret_cast<const float4*>(p.Hs[rb][2]);
+    float4* const wEx = reinterpret_cast<float4*>(p.Es[wb][0]);
+    float4* const wEy = reinterpret_cast<float4*>(p.Es[wb][1]);
+    float4* const wEz = reinterpret_cast<float4*>(p.Es[wb][2]);
+    float4* const wHx = reinterpret_cast<float4*>(p.Hs[wb][0]);
+    float4* const wHy = reinterpret_cast<float4*>(p.Hs[wb][1]);
+    float4* const wHz = reinterpret_cast<float4*>(p.Hs[wb][2]);
+    const float4* const rPx = reinterpret_cast<const float4*>(p.psiHs[rb][0]);
+    const float4* const rPy = reinterpret_cast<const float4*>(p.psiHs[rb][1]);
+    float4* const wPx = reinterpret_cast<float4*>(p.psiHs[wb][0]);
+    float4* const wPy = reinterpret_cast<float4*>(p.psiHs[wb][1]);
+    float4* const ePx = reinterpret_cast<float4*>(p.psiE[0]);
+    float4* const ePy = reinterpret_cast<float4*>(p.psiE[1]);
+    const float4* const Bx = reinterpret_cast<const float4*>(p.B[0]);
+    const float4* const By = reinterpret_cast<const float4*>(p.B[1]);
+    const float4* const Bz = reinterpret_cast<const float4*>(p.B[2]);
+
+    // The loads of iteration `it` read planes up to sweep index it+1 of the previous stage, which
+    // must therefore have finished it+2 indices on tiles t-1, t, t+1 (the k+3 rule), and must not
+    // run more than max_lead indices ahead of the next stage (keeps the window inside L2).
+    auto wait_deps = [&](int it) -> bool {
+      const unsigned need = has_prev ? base_prev + (unsigned)min(it + 2, X) : 0u;
+      const int lead = min(it, X) - 1 - cfg.max_lead;
+      const unsigned need_next = (has_next && lead > 0) ? base_mine + (unsigned)lead : 0u;
+      return spin([&]() { return ld_vol_s(&ctl.avail) >= need && ld_vol_s(&ctl.next) >= need_next; });
+    };
+
+    // Async copies of iteration `it` (plane PL): E[PL+1] -> E slot se; H, B, psi, absorber row
+    // of PL -> H/B slot sh.  `ecoef` = the iteration performs an E half-step (it >= 1).
+    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first, bool ecoef) {
+      const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
+      float4* const d = se + q;
+      float4* const h = sh + q;
+      cp_async16(d + 0 * ZQ, rEx + (vN + tvA));
+      cp_async16(d + 3 * ZQ, rEz + (vN + tvA));
+      cp_async16(d + 6 * ZQ, rEy + (vN + tvA));
+      cp_async16(d + 1 * ZQ, rEx + (vN + tvB));
+      cp_async16(d + 4 * ZQ, rEz + (vN + tvB));
+      cp_async16(h + 0 * ZQ, rHx + (vP + tvA));
+      cp_async16(h + 2 * ZQ, rHy + (vP + tvA));
+      cp_async16(h + 4 * ZQ, rHz + (vP + tvA));
+      if (doHB) {
+        cp_async16(d + 7 * ZQ, rEy + (vN + tvB));
+        cp_async16(d + 2 * ZQ, rEx + (vN + tvC));
+        cp_async16(d + 5 * ZQ, rEz + (vN + tvC));
+        cp_async16(h + 1 * ZQ, rHx + (vP + tvB));
+        cp_async16(h + 3 * ZQ, rHy + (vP + tvB));
+        cp_async16(h + 5 * ZQ, rHz + (vP + tvB));
+      }
+      if (ecoef) {
+        if (ownA) {
+          cp_async16(h + 6 * ZQ, Bx + (vP + tvA));
+          cp_async16(h + 8 * ZQ, By + (vP + tvA));
+          cp_async16(h + 10 * ZQ, Bz + (vP + tvA));
+        }
+        if (doHB) {
+          cp_async16(h + 7 * ZQ, Bx + (vP + tvB));
+          cp_async16(h + 9 * ZQ, By + (vP + tvB));
+          cp_async16(h + 11 * ZQ, Bz + (vP + tvB));
+        }
+        if (lane < 2 && (lane == 0 ? ownA : doHB))
+          cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
+                     A4 + ((unsigned)PL * (unsigned)Y + (lane == 0 ? yA : yB)));
+      }
+      if (has_psi) {
+        float4* const ps = sh + kLeanHRows * ZQ + slot;
+        const unsigned pp = (unsigned)PL * PPn;
+        cp_async16(ps, rPx + (pp + pvA));
+        cp_async16(ps + 2 * psi_row, rPy + (pp + pvA));
+        if (doHB) {
+          cp_async16(ps + psi_row, rPx + (pp + pvB));
+          cp_async16(ps + 3 * psi_row, rPy + (pp + pvB));
+        }
+        if (ecoef) {
+          if (ownA) {
+            cp_async16(ps + 4 * psi_row, ePx + (pp + pvA));
+            cp_async16(ps + 6 * psi_row, ePy + (pp + pvA));
+          }
+          if (doHB) {
+            cp_async16(ps + 5 * psi_row, ePx + (pp + pvB));
+            cp_async16(ps + 7 * psi_row, ePy + (pp + pvB));
+          }
+        }
+      }
+      if (se_first) {                                // very first plane of the sweep: E[PL] too
+        float4* const f = se_first + q;
+        cp_async16(f + 0 * ZQ, rEx + (vP + tvA));
+        cp_async16(f + 3 * ZQ, rEz + (vP + tvA));
+        cp_async16(f + 6 * ZQ, rEy + (vP + tvA));
+        cp_async16(f + 1 * ZQ, rEx + (vP + tvB));
+        cp_async16(f + 4 * ZQ, rEz + (vP + tvB));
+        if (doHB) {
+          cp_async16(f + 7 * ZQ, rEy + (vP + tvB));
+          cp_async16(f + 2 * ZQ, rEx + (vP + tvC));
+          cp_async16(f + 5 * ZQ, rEz + (vP + tvC));
+        }
+      }
+    };
+
+    int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
+    float4* sprev = wbase;                         // slot holding E[P]
+    float4* scur = wbase + eslot_f4;               // slot holding E[P+1]
+    float4* snext = wbase + 2 * eslot_f4;          // slot being filled with E[P+2]
+    float4* hcur = hbase;                          // slot holding H, B, psi, absorber row of P
+    float4* hnext = hbase + hslot_f4;              // ... being filled for P+1
+    ok = wait_deps(0);
+    if (ok) issue(P, P + 1 == X ? 0 : P + 1, scur, hcur, sprev, false);
+    cp_async_commit();
+
+    float hypA[VW], hzpA[VW], hypB[VW], hzpB[VW];  // H^{n+1/2}[P-1] of the thread's own cells
+#pragma unroll
+    for (int v = 0; v < VW; ++v) { hypA[v] = 0.f; hzpA[v] = 0.f; hypB[v] = 0.f; hzpB[v] = 0.f; }
+
+#pragma unroll U
+    for (int i = 0; i <= X && ok; ++i) {
+      const bool real = i >= 1;
+      const int Pn = P + 1 == X ? 0 : P + 1;
+      const unsigned vP = (unsigned)P * PVn;
+      cp_async_wait<0>();                          // this lane's copies of iteration i have landed
+      if (i < X) {
+        ok = wait_deps(i + 1);
+        if (!ok) break;
+        issue(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, hnext, nullptr, true);
+      }
+      cp_async_commit();
+      __syncwarp();                                // the absorber rows were copied by lanes 0, 1
+      if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
+
+      const unsigned pP = (unsigned)P * PPn;
+
+      // ---------------------------------- H half-step ---------------------------------------------
+      const float4* const ep = sprev + q;
+      const float4* const ec = scur + q;
+      const float4* const hc = hcur + q;
+      const float4* const pc = hcur + kLeanHRows * ZQ + (has_psi ? slot : 0);
+      float exA[VW], eyA[VW], ezA[VW], exB[VW], eyB[VW], ezB[VW];
+      float hxA[VW], hyA[VW], hzA[VW], hxB[VW], hyB[VW], hzB[VW];
+      float psxA[VW], psyA[VW], psxB[VW], psyB[VW];
+      {
+        float exC[VW], ezC[VW], eyxA[VW], ezxA[VW], eyxB[VW], ezxB[VW];
+        f4_to_arr(lds16(ep + 0 * ZQ), exA); f4_to_arr(lds16(ep + 3 * ZQ), ezA);
+        f4_to_arr(lds16(ep + 6 * ZQ), eyA);
+        f4_to_arr(lds16(ep + 1 * ZQ), exB); f4_to_arr(lds16(ep + 4 * ZQ), ezB);
+        f4_to_arr(lds16(ep + 7 * ZQ), eyB);
+        f4_to_arr(lds16(ep + 2 * ZQ), exC); f4_to_arr(lds16(ep + 5 * ZQ), ezC);
+        f4_to_arr(lds16(ec + 6 * ZQ), eyxA); f4_to_arr(lds16(ec + 3 * ZQ), ezxA);
+        f4_to_arr(lds16(ec + 7 * ZQ), eyxB); f4_to_arr(lds16(ec + 4 * ZQ), ezxB);
+        f4_to_arr(lds16(hc + 0 * ZQ), hxA); f4_to_arr(lds16(hc + 2 * ZQ), hyA);
+        f4_to_arr(lds16(hc + 4 * ZQ), hzA);
+        f4_to_arr(lds16(hc + 1 * ZQ), hxB); f4_to_arr(lds16(hc + 3 * ZQ), hyB);
+        f4_to_arr(lds16(hc + 5 * ZQ), hzB);
+#pragma unroll
+        for (int v = 0; v < VW; ++v) { psxA[v] = 0.f; psyA[v] = 0.f; psxB[v] = 0.f; psyB[v] = 0.f; }
+        if (has_psi) {
+          f4_to_arr(lds16(pc), psxA); f4_to_arr(lds16(pc + 2 * psi_row), psyA);
+          f4_to_arr(lds16(pc + psi_row), psxB); f4_to_arr(lds16(pc + 3 * psi_row), psyB);
+        }
+        float exA_top = __shfl_down_sync(0xffffffffu, exA[0], 1);
+        float eyA_top = __shfl_down_sync(0xffffffffu, eyA[0], 1);
+        float exB_top = __shfl_down_sync(0xffffffffu, exB[0], 1);
+        float eyB_top = __shfl_down_sync(0xffffffffu, eyB[0], 1);
+        if (top) { exA_top = 0.f; eyA_top = 0.f; exB_top = 0.f; eyB_top = 0.f; }
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+          const float exz = (v + 1 < VW) ? exA[(v + 1) % VW] : exA_top;
+          const float eyz = (v + 1 < VW) ? eyA[(v + 1) % VW] : eyA_top;
+          h_cell(exA[v], eyA[v], ezA[v], exz, eyz, ezB[v], exB[v], eyxA[v], ezxA[v], ah[v], bh[v],
+                 ikh[v], dt, psxA[v], psyA[v], hxA[v], hyA[v], hzA[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+          const float exz = (v + 1 < VW) ? exB[(v + 1) % VW] : exB_top;
+          const float eyz = (v + 1 < VW) ? eyB[(v + 1) % VW] : eyB_top;
+          h_cell(exB[v], eyB[v], ezB[v], exz, eyz, ezC[v], exC[v], eyxB[v], ezxB[v], ah[v], bh[v],
+                 ikh[v], dt, psxB[v], psyB[v], hxB[v], hyB[v], hzB[v]);
+        }
+      }
+      // boundary H for the next warp: wait until it has consumed the slot's previous content
+      {
+        float4* const xs = xmine + (kk & (kLeanXR - 1)) * 2 * ZQ;
+        if (kk >= (unsigned)kLeanXR && w + 1 < NWt) {
+          const unsigned need = kk + 1u - (unsigned)kLeanXR;
+          ok = spin([&]() { return ld_vol_s(&ctl.rcnt[w]) >= need; });
+          if (!ok) break;
+        }
+        xs[0] = arr_to_f4(hzB);
+        xs[ZQ] = arr_to_f4(hxB);
+        __syncwarp();
+        if (lane == 0) st_vol_s(&ctl.hcnt[w], kk + 1u);
+      }
+
+      // ---------------------------------- E half-step ---------------------------------------------
+      if (real) {
+        float hzmA[VW], hxmA[VW];                  // (Hz, Hx) of the column before the pair
+        if (w > 0) {
+          const unsigned need = kk + 1u;
+          ok = spin([&]() { return ld_vol_s(&ctl.hcnt[w - 1]) >= need; });
+          if (!ok) break;
+          const float4* const xs = xprev + (kk & (kLeanXR - 1)) * 2 * ZQ;
+          f4_to_arr(lds16(xs), hzmA); f4_to_arr(lds16(xs + ZQ), hxmA);
+          __syncwarp();
+          if (lane == 0) st_vol_s(&ctl.rcnt[w - 1], kk + 1u);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VW; ++v) { hzmA[v] = 0.f; hxmA[v] = 0.f; }
+        }
+        float hxA_bot = __shfl_up_sync(0xffffffffu, hxA[VW - 1], 1);
+        float hyA_bot = __shfl_up_sync(0xffffffffu, hyA[VW - 1], 1);
+        float hxB_bot = __shfl_up_sync(0xffffffffu, hxB[VW - 1], 1);
+        float hyB_bot = __shfl_up_sync(0xffffffffu, hyB[VW - 1], 1);
+        if (bottom) { hxA_bot = 0.f; hyA_bot = 0.f; hxB_bot = 0.f; hyB_bot = 0.f; }
+        if (ownA) {
+          float b0[VW], b1[VW], b2[VW], qsx[VW], qsy[VW];
+          f4_to_arr(lds16(hc + 6 * ZQ), b0); f4_to_arr(lds16(hc + 8 * ZQ), b1);
+          f4_to_arr(lds16(hc + 10 * ZQ), b2);
+          const float4 aA = lds16(hcur + kLeanHRows * ZQ + 8 * psi_row);
+#pragma unroll
+          for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
+          if (has_psi) { f4_to_arr(lds16(pc + 4 * psi_row), qsx); f4_to_arr(lds16(pc + 6 * psi_row), qsy); }
+#pragma unroll
+          for (int v = 0; v < VW; ++v) {
+            const float hxz = (v > 0) ? hxA[(v + VW - 1) % VW] : hxA_bot;
+            const float hyz = (v > 0) ? hyA[(v + VW - 1) % VW] : hyA_bot;
+            e_cell(hxA[v], hyA[v], hzA[v], hxz, hyz, hzmA[v], hxmA[v], hypA[v], hzpA[v], ae[v], be[v],
+                   ike[v], aA.x, aA.y, aA.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], exA[v], eyA[v], ezA[v]);
+          }
+          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcA)
+            add_source<VW>(g, p.src, w0, w1, P, yA, q, exA, eyA, ezA);
+          const unsigned o = vP + tvA;
+          __stcg(wHx + o, arr_to_f4(hxA)); __stcg(wHy + o, arr_to_f4(hyA)); __stcg(wHz + o, arr_to_f4(hzA));
+          __stcg(wEx + o, arr_to_f4(exA)); __stcg(wEy + o, arr_to_f4(eyA)); __stcg(wEz + o, arr_to_f4(ezA));
+          if (has_psi) {
+            __stcg(wPx + (pP + pvA), arr_to_f4(psxA)); __stcg(wPy + (pP + pvA), arr_to_f4(psyA));
+            __stcg(ePx + (pP + pvA), arr_to_f4(qsx)); __stcg(ePy + (pP + pvA), arr_to_f4(qsy));
+          }
+          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yA, q, exA, eyA, ezA);
+        }
+        if (doHB) {
+          float b0[VW], b1[VW], b2[VW], qsx[VW], qsy[VW];
+          f4_to_arr(lds16(hc + 7 * ZQ), b0); f4_to_arr(lds16(hc + 9 * ZQ), b1);
+          f4_to_arr(lds16(hc + 11 * ZQ), b2);
+          const float4 aB = lds16(hcur + kLeanHRows * ZQ + 8 * psi_row + 1);
+#pragma unroll
+          for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
+          if (has_psi) { f4_to_arr(lds16(pc + 5 * psi_row), qsx); f4_to_arr(lds16(pc + 7 * psi_row), qsy); }
+#pragma unroll
+          for (int v = 0; v < VW; ++v) {
+            const float hxz = (v > 0) ? hxB[(v + VW - 1) % VW] : hxB_bot;
+            const float hyz = (v > 0) ? hyB[(v + VW - 1) % VW] : hyB_bot;
+            e_cell(hxB[v], hyB[v], hzB[v], hxz, hyz, hzA[v], hxA[v], hypB[v], hzpB[v], ae[v], be[v],
+                   ike[v], aB.x, aB.y, aB.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], exB[v], eyB[v], ezB[v]);
+          }
+          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcB)
+            add_source<VW>(g, p.src, w0, w1, P, yB, q, exB, eyB, ezB);
+          const unsigned o = vP + tvB;
+          __stcg(wHx + o, arr_to_f4(hxB)); __stcg(wHy + o, arr_to_f4(hyB)); __stcg(wHz + o, arr_to_f4(hzB));
+          __stcg(wEx + o, arr_to_f4(exB)); __stcg(wEy + o, arr_to_f4(eyB)); __stcg(wEz + o, arr_to_f4(ezB));
+          if (has_psi) {
+            __stcg(wPx + (pP + pvB), arr_to_f4(psxB)); __stcg(wPy + (pP + pvB), arr_to_f4(psyB));
+            __stcg(ePx + (pP + pvB), arr_to_f4(qsx)); __stcg(ePy + (pP + pvB), arr_to_f4(qsy));
+          }
+          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yB, q, exB, eyB, ezB);
+        }
+        // every store of sweep indices <= i has been issued by this warp
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          st_vol_s(&ctl.wdone[w], base_mine + (unsigned)i);
+        }
+      } else if (w > 0 && lane == 0) {
+        st_vol_s(&ctl.rcnt[w - 1], kk + 1u);       // prologue plane: nothing to consume
+      }
+#pragma unroll
+      for (int v = 0; v < VW; ++v) { hypA[v] = hyA[v]; hzpA[v] = hzA[v]; hypB[v] = hyB[v]; hzpB[v] = hzB[v]; }
+      P = Pn;
+      float4* const tmp = sprev; sprev = scur; scur = snext; snext = tmp;
+      float4* const tmh = hcur; hcur = hnext; hnext = tmh;
+      ++kk;
+    }
+    cp_async_wait<0>();
+    iters_done += (unsigned)X + 1u;
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (lane == 0) atomicAdd(&ctl.exited, 1u);
+}
+
+// Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.
+inline int lean_warps(int tile_y) { return (tile_y + 2) / 2; }
+
+inline size_t lean_smem_bytes(const Geom& g, int tile_y) {
+  const size_t eslot_f4 = (size_t)kLeanERows * 32;
+  const size_t hslot_f4 = (size_t)kLeanHRows * 32 + 8 * (size_t)g.npg + 2;
+  const size_t warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + (size_t)kLeanXR * 2 * 32;
+  return sizeof(float4) * warp_f4 * lean_warps(tile_y);
+}
+
+inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stages_req, int sms,
+                           int l2_bytes, SystolicCfg* cfg, std::string* why) {
+  if (reduced) { *why = "fp32 storage only"; return false; }
+  if (g.Zq != 32) { *why = "needs a z-column of exactly 32 vectors (125 <= Z <= 128)"; return false; }
+  if (g.N / 4 * 3 >= (1ll << 32)) { *why = "domain too large for 32-bit vector indices"; return false; }
+  int max_tile = 2 * kLeanMaxWarps - 1;          // 2*NW - 1 owned columns fill NW warps exactly
+  while (max_tile >= 1 && lean_smem_bytes(g, max_tile) + 256 > 227 * 1024) --max_tile;
+  if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
+  if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
+  if (max_tile > g.Y) max_tile = g.Y;
+  const int ntiles = (g.Y + max_tile - 1) / max_tile;
+  const int widest = (g.Y + ntiles - 1) / ntiles;
+  cfg->tile_y = widest;
+  cfg->ntiles = ntiles;
+  cfg->cols = 2;
+  cfg->threads = 32 * (lean_warps(widest) + 1);
+  cfg->smem_bytes = (int)lean_smem_bytes(g, widest);
+  cfg->max_lead = 10;
+  cfg->pf_ahead = 6;
+  cfg->svc_sleep_ns = 200;
+  if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
+  if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
+  if (const char* e = getenv("B200FDTD_SVC_SLEEP")) cfg->svc_sleep_ns = atoi(e);
+  if (cfg->max_lead < 6) cfg->max_lead = 6;
+  if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
+  cfg->trap_on_timeout = 1;
+  int occ = 0;
+  cfg->need_zfix = 1;                            // (re-used) unroll factor of the plane loop
+  if (const char* e = getenv("B200FDTD_LEAN_UNROLL")) cfg->need_zfix = atoi(e) == 2 ? 2 : 1;
+  const void* fn = cfg->need_zfix == 2 ? (const void*)lean_kernel<2> : (const void*)lean_kernel<1>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
+          cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    *why = "kernel does not fit on an SM";
+    return false;
+  }
+  const long long capacity = (long long)occ * sms;
+  if (ntiles > capacity) { *why = "more y-tiles than co-resident CTAs"; return false; }
+  int stages = (int)(capacity / ntiles);
+  const long long plane_bytes = g.P * 4ll * 15;
+  const int lag = 6;                             // planes a stage trails its predecessor by
+  long long by_l2 = (long long)(l2_bytes * 0.7) / (lag * plane_bytes);
+  if (by_l2 < 1) by_l2 = 1;
+  if (stages > by_l2) stages = (int)by_l2;
+  if (stages_req > 0 && stages_req <= capacity / ntiles) stages = stages_req;
+  if (stages > g.tt) stages = g.tt > 0 ? g.tt : 1;
+  if (stages > g.X) stages = g.X;
+  cfg->stages = stages;
+  cfg->l2_window_bytes = (long long)stages * lag * plane_bytes;
+  return true;
+}
+
+inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& cfg, unsigned* sync,
+                       cudaStream_t st) {
+  const void* fn = cfg.need_zfix == 2 ? (const void*)lean_kernel<2> : (const void*)lean_kernel<1>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       cfg.smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  Geom gg = g;
+  Ptrs<float> pp = p;
+  SystolicCfg cc = cfg;
+  void* args[] = {&gg, &pp, &cc, &sync};
+  e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles), dim3(cfg.threads), args,
+                                  cfg.smem_bytes, st);
+  if (e != cudaSuccess) return (int)e;
+  systolic_check_kernel<<<1, 1, 0, st>>>(sync + (size_t)cfg.stages * cfg.ntiles * kSysFlagStride);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b200

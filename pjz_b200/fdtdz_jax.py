@@ -28,7 +28,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fdtd.so")
 
 NUM_INPUTS = 7
-_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2, "systolic_async": 3, "systolic_tma": 4}
+_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2, "systolic_async": 3, "systolic_tma": 4,
+            "systolic_lean": 5}
 ABI_VERSION = 1
 
 

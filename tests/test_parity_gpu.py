@@ -115,6 +115,37 @@ def test_systolic_tma_tilings(tile_y, stages, prefetch):
   np.testing.assert_array_equal(out, want)
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (6, 3), (4, 40), (13, 2)])
+def test_systolic_lean_tilings(tile_y, stages, axis):
+  """The warp-per-column-pair kernel (fp32, z-column of exactly 32 vectors): every tiling, all
+  source orientations, bit-exact against the C oracle."""
+  kw = random_problem(domain=(11, 23, 128), axis=axis, pml=(16, 16), tt=45, seed=13,
+                      output_steps=(20, 45, 6))
+  want = fdtd_c.fdtdz(**kw)
+  out = run_gpu(kw, kernel="systolic_lean", tile_y=tile_y, stages=stages)
+  np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("domain,pml,zb", [((9, 14, 125), (3, 5), False), ((16, 1, 128), (0, 0), False),
+                                           ((5, 2, 127), (10, 12), False), ((12, 26, 128), (0, 0), True),
+                                           ((3, 30, 126), (16, 16), False), ((2, 5, 128), (4, 4), False)])
+def test_systolic_lean_ragged_domains(domain, pml, zb):
+  for axis in (0, 1, 2):
+    kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
+                        seed=7, output_steps=(5, 14, 4), absorb_pad=2, z_as_batch=zb)
+    np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean"), fdtd_c.fdtdz(**kw))
+
+
+def test_systolic_lean_rejects_other_geometries():
+  kw = random_problem(domain=(8, 8, 64), tt=4, seed=1)
+  with pytest.raises((ValueError, RuntimeError)):
+    run_gpu(kw, kernel="systolic_lean")
+  kw = random_problem(domain=(8, 8, 128), tt=4, seed=1, reduced=True)
+  with pytest.raises((ValueError, RuntimeError)):
+    run_gpu(kw, kernel="systolic_lean")
+
+
 @pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (5, 3), (14, 7), (4, 40)])
 def test_systolic_tilings(tile_y, stages):
   """Every tiling / pipeline depth must give the same bits (many stages on a short x extent
@@ -177,6 +208,7 @@ def test_schedule_selection_and_linearity_large():
   np.testing.assert_array_equal(a, b)
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_async"))
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_tma"))
+  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean"))
   assert np.isfinite(a).all() and np.abs(a).max() > 0
   kw2 = dict(kw); kw2["output_steps"] = (5, 16, 10)
   np.testing.assert_array_equal(run_gpu(kw2), a[1:4:2])
