@@ -148,8 +148,9 @@ static bool configure_tma(const Geom& g, const b200fdtd_desc* d, int depth, int 
   return false;
 }
 
-// AUTO: cp.async-staged systolic kernel (prefetch distance 1 measured fastest: a deeper ring
-// only shrinks the tile), else the register-staged one, else the per-step kernels.
+// AUTO: the warp-per-column-pair kernel when the geometry allows it (fp32, 32 z-vectors), else the
+// cp.async-staged systolic kernel (prefetch distance 1 measured fastest: a deeper ring only
+// shrinks the tile), else the register-staged one, else the per-step kernels.
 template <typename T>
 static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   plan->kernel = d->kernel;
@@ -170,6 +171,12 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
     if (!configure_tma<T>(g, d, depth, sms, l2, &plan->sys, &why))
       return fail(B200FDTD_EUNSUPPORTED, "systolic_tma kernel unavailable: %s", why.c_str());
     plan->depth = depth;
+    return B200FDTD_OK;
+  }
+  if (d->kernel == B200FDTD_KERNEL_AUTO &&
+      lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
+    plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
+    plan->depth = 1;
     return B200FDTD_OK;
   }
   if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {

@@ -62,7 +62,8 @@ __device__ __forceinline__ float4 arr_to_f4(const float (&v)[4]) {
 }
 
 // U = unroll factor of the plane loop (2 removes the loop-carried register moves).
-template <int U>
+// STATS = per-warp wait-time accounting printed at the end (debug builds of the plan only).
+template <int U, bool STATS>
 __global__ void __launch_bounds__(32 * (kLeanMaxWarps + 1), 1)
 lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync) {
   constexpr int VW = 4;
@@ -192,19 +193,24 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const float dt = g.dt;
   const float4* const A4 = reinterpret_cast<const float4*>(p.A4);
 
+  long long st_cp = 0, st_avail = 0, st_next = 0, st_rc = 0, st_hc = 0;
+  const long long st_begin = STATS ? clock64() : 0;
   bool ok = true;
   unsigned kk = 0;                                 // cumulative iteration count (never reset)
   unsigned iters_done = 0;
 
-  // Spin (all lanes, warp-uniform verdict) until cond() holds; false = give up.
+  // Spin (all lanes, warp-uniform verdict) until cond() holds; false = give up.  The slow path
+  // backs off with nanosleep so that a waiting warp leaves the issue slots (and the power
+  // budget) to the warp it shares its scheduler with.
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
     unsigned long long t0 = 0;
-    unsigned spins = 0;
+    unsigned spins = 0, ns = 20;
     while (true) {
+      __nanosleep(ns);
       if (__all_sync(0xffffffffu, cond())) return true;
       if (__any_sync(0xffffffffu, ld_vol_s(&ctl.ok) == 0)) return false;
-      __nanosleep(32);                             // leave the issue slots to the other warps
+      if (ns < (unsigned)cfg.spin_ns_max) ns += ns;
       if ((++spins & 255u) == 0) {
         const unsigned long long now = globaltimer_ns();
         if (t0 == 0) t0 = now;
@@ -254,6 +260,14 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       const unsigned need = has_prev ? base_prev + (unsigned)min(it + 2, X) : 0u;
       const int lead = min(it, X) - 1 - cfg.max_lead;
       const unsigned need_next = (has_next && lead > 0) ? base_mine + (unsigned)lead : 0u;
+      if constexpr (STATS) {
+        const long long c0 = clock64();
+        const bool r0 = spin([&]() { return ld_vol_s(&ctl.avail) >= need; });
+        const long long c1 = clock64();
+        const bool r1 = r0 && spin([&]() { return ld_vol_s(&ctl.next) >= need_next; });
+        st_avail += c1 - c0; st_next += clock64() - c1;
+        return r1;
+      }
       return spin([&]() { return ld_vol_s(&ctl.avail) >= need && ld_vol_s(&ctl.next) >= need_next; });
     };
 
@@ -348,6 +362,11 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       const bool real = i >= 1;
       const int Pn = P + 1 == X ? 0 : P + 1;
       const unsigned vP = (unsigned)P * PVn;
+      if constexpr (STATS) {
+        const long long c0 = clock64();
+        cp_async_wait<0>();
+        st_cp += clock64() - c0;
+      }
       cp_async_wait<0>();                          // this lane's copies of iteration i have landed
       if (i < X) {
         ok = wait_deps(i + 1);
@@ -412,7 +431,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         float4* const xs = xmine + (kk & (kLeanXR - 1)) * 2 * ZQ;
         if (kk >= (unsigned)kLeanXR && w + 1 < NWt) {
           const unsigned need = kk + 1u - (unsigned)kLeanXR;
+          const long long c0 = STATS ? clock64() : 0;
           ok = spin([&]() { return ld_vol_s(&ctl.rcnt[w]) >= need; });
+          if constexpr (STATS) st_rc += clock64() - c0;
           if (!ok) break;
         }
         xs[0] = arr_to_f4(hzB);
@@ -426,7 +447,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         float hzmA[VW], hxmA[VW];                  // (Hz, Hx) of the column before the pair
         if (w > 0) {
           const unsigned need = kk + 1u;
+          const long long c0 = STATS ? clock64() : 0;
           ok = spin([&]() { return ld_vol_s(&ctl.hcnt[w - 1]) >= need; });
+          if constexpr (STATS) st_hc += clock64() - c0;
           if (!ok) break;
           const float4* const xs = xprev + (kk & (kLeanXR - 1)) * 2 * ZQ;
           f4_to_arr(lds16(xs), hzmA); f4_to_arr(lds16(xs + ZQ), hxmA);
@@ -514,7 +537,20 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   }
   cp_async_wait<0>();
   __syncwarp();
+  if constexpr (STATS) {
+    if (lane == 0 && (t == 0 || t == NT / 2)) {
+      const double tot = (double)(clock64() - st_begin);
+      printf("leanstats j %d t %d w %d iters %u cyc/iter %.0f  cp %.3f avail %.3f next %.3f rcnt %.3f hcnt %.3f\n",
+             j, t, w, kk, tot / (kk ? kk : 1), st_cp / tot, st_avail / tot, st_next / tot,
+             st_rc / tot, st_hc / tot);
+    }
+  }
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
+}
+
+inline const void* lean_fn(int unroll, bool stats) {
+  if (stats) return (const void*)lean_kernel<1, true>;
+  return unroll == 2 ? (const void*)lean_kernel<2, false> : (const void*)lean_kernel<1, false>;
 }
 
 // Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.
@@ -547,6 +583,8 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   cfg->max_lead = 10;
   cfg->pf_ahead = 6;
   cfg->svc_sleep_ns = 200;
+  cfg->spin_ns_max = 160;
+  if (const char* e = getenv("B200FDTD_SPIN_NS")) cfg->spin_ns_max = atoi(e);
   if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
   if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
   if (const char* e = getenv("B200FDTD_SVC_SLEEP")) cfg->svc_sleep_ns = atoi(e);
@@ -556,7 +594,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   int occ = 0;
   cfg->need_zfix = 1;                            // (re-used) unroll factor of the plane loop
   if (const char* e = getenv("B200FDTD_LEAN_UNROLL")) cfg->need_zfix = atoi(e) == 2 ? 2 : 1;
-  const void* fn = cfg->need_zfix == 2 ? (const void*)lean_kernel<2> : (const void*)lean_kernel<1>;
+  const void* fn = lean_fn(cfg->need_zfix, getenv("B200FDTD_LEAN_STATS") != nullptr);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -583,7 +621,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
 
 inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& cfg, unsigned* sync,
                        cudaStream_t st) {
-  const void* fn = cfg.need_zfix == 2 ? (const void*)lean_kernel<2> : (const void*)lean_kernel<1>;
+  const void* fn = lean_fn(cfg.need_zfix, getenv("B200FDTD_LEAN_STATS") != nullptr);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;

@@ -47,6 +47,7 @@ struct SystolicCfg {
   int pf_ahead;          // systolic_async: planes of L2 prefetch beyond the staging ring
   int svc_sleep_ns;      // systolic_async: back-off of the poller / publisher warps
   int cols;              // systolic_async: adjacent columns per compute thread (1 or 2)
+  int spin_ns_max;       // systolic_lean: back-off ceiling of a waiting compute warp
   long long l2_window_bytes;
 };
 

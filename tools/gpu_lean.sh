@@ -10,7 +10,7 @@ try:
 except Exception as e: print('ERR',e)"; }
 {
 ENVV=""
-run --kernel systolic_lean --tt 500
-run --kernel systolic_async
+run --kernel systolic_lean --tt 1000
+run --kernel systolic_lean
 while IFS= read -r line; do [ -n "$line" ] && run $line; done < ${VARFILE:-/dev/null}
 } | tee gpurun_out/quick_lean.log
