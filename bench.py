@@ -319,15 +319,16 @@ def main():
   achieved = per_gpu * bpc                       # GB/s of ALGORITHMIC traffic
   traffic = ncu_traffic()
   if info["kernel"].startswith("systolic"):
-    dominant = (("systolic2_kernel" if info["kernel"] == "systolic_async" else "systolic_kernel") +
-                " (1 launch per engine call; duration = call time incl. 3 prep kernels)")
+    kname = {"systolic_lean": "lean_kernel", "systolic_async": "systolic2_kernel",
+             "systolic_tma": "systolic3_kernel"}.get(info["kernel"], "systolic_kernel")
+    dominant = kname + " (1 launch per engine call; duration = call time incl. 3 prep kernels)"
     launches = (3 + 2) * args.steps
   else:
     dominant = "twopass_h_kernel + twopass_e_kernel (2 launches per FDTD step)"
     launches = (3 + 2 * tt) * args.steps
   per_launch_updates = cells * (tt if info["kernel"].startswith("systolic") else 0.5)
-  # ncu DRAM bytes are only quoted for the configuration they were captured on
-  have_traffic = (traffic is not None and info["kernel"] == "systolic_async" and
+  # ncu DRAM bytes are only quoted for the kernel and configuration they were captured on
+  have_traffic = (traffic is not None and traffic.get("plan_kernel") == info["kernel"] and
                   args.workload == "bend" and not args.reduced)
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
               "frac": achieved / peak,

@@ -54,6 +54,11 @@ struct LeanCtl {
 
 __device__ __forceinline__ float4 lds16(const float4* p) { return *p; }
 
+// The 128-byte line at p is dead: drop it from L2 without writing it back.
+__device__ __forceinline__ void discard_l2_line(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 __device__ __forceinline__ void f4_to_arr(const float4 r, float (&v)[4]) {
   v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
 }
@@ -135,6 +140,14 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
           const unsigned sweep = pf_done / sweep_iters, it = pf_done % sweep_iters;
           const int n = j + (int)sweep * S;
           if (n >= g.tt) break;
+          // Only planes the previous step has already produced: prefetching a plane that is
+          // about to be overwritten would fetch dead data from HBM.  (A follower finds them in
+          // L2 anyway; the prefetch matters for the stage that leads the window.)
+          if (n > 0) {
+            const unsigned m = (unsigned)(n / S);
+            const unsigned need = (j > 0 ? m : m - 1u) * (unsigned)X + (unsigned)min((int)it + 2, X);
+            if (min(v0, min(v1, v2)) < need) break;
+          }
           const int rb = n & 1;
           const int P = wrapi(n % X - 1 + (int)it, X), Pn = wrapi(P + 1, X);
           const int a = lane - 8;
@@ -171,6 +184,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const unsigned pvA = (unsigned)yA * g.npg + (has_psi ? slot : 0);
   const unsigned pvB = (unsigned)yB * g.npg + (has_psi ? slot : 0);
   const bool top = q + 1 == ZQ, bottom = q == 0;
+  const bool discA = cA >= 2 && cA <= Yt - 1, discB = cB >= 2 && cB <= Yt - 1;
 
   float4* const wbase = smem + (size_t)w * warp_f4;
   float4* const hbase = wbase + 3 * eslot_f4;
@@ -376,6 +390,24 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       cp_async_commit();
       __syncwarp();                                // the absorber rows were copied by lanes 0, 1
       if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
+      // The field vectors that have just landed (E^n[P+1], H^{n-1/2}[P]) have now been read by
+      // their only reader -- columns 2 .. Yt-1 are loaded by no other tile, and every plane but
+      // the first one of the sweep is loaded exactly once -- and will be overwritten two steps
+      // later: drop the dirty lines from L2 instead of letting them be written back to HBM.
+      if (cfg.discard && i >= 1 && (q & 7) == 0) {
+        const unsigned vN = (unsigned)Pn * PVn;
+        if (discA) {                                 // (Ex, Ez of column A: see the E half-step)
+          discard_l2_line(rEy + (vN + tvA));
+          discard_l2_line(rHx + (vP + tvA)); discard_l2_line(rHy + (vP + tvA));
+          discard_l2_line(rHz + (vP + tvA));
+        }
+        if (discB) {
+          discard_l2_line(rEx + (vN + tvB)); discard_l2_line(rEy + (vN + tvB));
+          discard_l2_line(rEz + (vN + tvB));
+          discard_l2_line(rHx + (vP + tvB)); discard_l2_line(rHy + (vP + tvB));
+          discard_l2_line(rHz + (vP + tvB));
+        }
+      }
 
       const unsigned pP = (unsigned)P * PPn;
 
@@ -455,6 +487,12 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
           f4_to_arr(lds16(xs), hzmA); f4_to_arr(lds16(xs + ZQ), hxmA);
           __syncwarp();
           if (lane == 0) st_vol_s(&ctl.rcnt[w - 1], kk + 1u);
+          // warp w-1 has finished the H half-step of this iteration, i.e. its copy of this
+          // column's (Ex, Ez)[P+1] -- the only other reader -- has landed
+          if (cfg.discard && discA && (q & 7) == 0) {
+            const unsigned vN = (unsigned)Pn * PVn;
+            discard_l2_line(rEx + (vN + tvA)); discard_l2_line(rEz + (vN + tvA));
+          }
         } else {
 #pragma unroll
           for (int v = 0; v < VW; ++v) { hzmA[v] = 0.f; hxmA[v] = 0.f; }
@@ -584,6 +622,8 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   cfg->pf_ahead = 6;
   cfg->svc_sleep_ns = 200;
   cfg->spin_ns_max = 160;
+  cfg->discard = 1;
+  if (const char* e = getenv("B200FDTD_LEAN_DISCARD")) cfg->discard = atoi(e);
   if (const char* e = getenv("B200FDTD_SPIN_NS")) cfg->spin_ns_max = atoi(e);
   if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
   if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);

@@ -48,6 +48,7 @@ struct SystolicCfg {
   int svc_sleep_ns;      // systolic_async: back-off of the poller / publisher warps
   int cols;              // systolic_async: adjacent columns per compute thread (1 or 2)
   int spin_ns_max;       // systolic_lean: back-off ceiling of a waiting compute warp
+  int discard;           // systolic_lean: drop consumed field lines from L2 (discard.global.L2)
   long long l2_window_bytes;
 };
 
