@@ -36,7 +36,7 @@
 
 namespace b200 {
 
-constexpr int kLeanMaxWarps = 7;       // compute warps per CTA (255-register budget: 8 warps/SM)
+constexpr int kLeanMaxWarps = 8;       // compute warps per CTA (+1 service warp: 224 registers)
 constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
 constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
 constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
@@ -648,7 +648,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   int stages = (int)(capacity / ntiles);
   const long long plane_bytes = g.P * 4ll * 15;
   const int lag = 6;                             // planes a stage trails its predecessor by
-  long long by_l2 = (long long)(l2_bytes * 0.7) / (lag * plane_bytes);
+  long long by_l2 = (long long)(l2_bytes * 0.8) / (lag * plane_bytes);
   if (by_l2 < 1) by_l2 = 1;
   if (stages > by_l2) stages = (int)by_l2;
   if (stages_req > 0 && stages_req <= capacity / ntiles) stages = stages_req;
