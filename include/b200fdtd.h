@@ -155,7 +155,7 @@ int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info);
  * pjz_b200/_decomp.py exchanges halo planes between GPUs after every half-step.  A session
  * binds a descriptor, the input arrays and a caller-owned workspace (no internal allocation),
  * prepares the coefficients, and then advances one half-step per call with the per-step
- * kernels, in place.  Between calls the caller may read and write field planes directly in the
+ * kernels, in place (or whole steps with b200fdtd_session_advance, below).  Between calls the caller may read and write field planes directly in the
  * workspace (b200fdtd_session_layout says where they are).  Everything is ordered on the
  * stream passed to each call.  There is no reference counterpart (fdtd-z is single-GPU). */
 typedef struct b200fdtd_session b200fdtd_session;
@@ -176,6 +176,22 @@ int b200fdtd_session_step_e(b200fdtd_session* session, int n, void* stream);
  *            padded z extent Zp, bytes per element, X, Y}: component c of E lives at
  *            workspace + info[0] + c*info[2], laid out [X][Y][Zp]. */
 int b200fdtd_session_layout(const b200fdtd_session* session, int64_t* info);
+
+/* Whole steps [n0, n0+nsteps) in one call.  A session whose descriptor selects
+ * B200FDTD_KERNEL_AUTO / _SYSTOLIC_LEAN on a geometry that kernel supports runs them as ONE
+ * persistent launch of the systolic kernel (the y-slab decomposition with ghost zones of
+ * pjz_b200/_decomp.py advances G steps between halo exchanges); its state is ping-ponged: the
+ * fields and psiH after n steps live in buffer set n & 1 (psiE is updated in place).  Other
+ * sessions loop over step_h / step_e.  step_h / step_e are refused on a systolic session. */
+int b200fdtd_session_advance(b200fdtd_session* session, int n0, int nsteps, void* stream);
+
+/* info[16]: entries 0..7 as b200fdtd_session_layout, then
+ *   [8]  byte offset of Ex of buffer set 1 (-1: per-step session, single set)
+ *   [9]  byte offset of psiH[0] of set 0; psiH[1], psiE[0], psiE[1] follow at multiples of [10]
+ *   [10] bytes per psi array, laid out [X][Y][info[12]] floats (only the PML z-groups)
+ *   [11] byte offset of psiH[0] of set 1 (-1: single set)      [12] psi floats per column
+ *   [13] 1 if the state is ping-ponged (systolic session)      [14] kernel   [15] stages */
+int b200fdtd_session_layout2(const b200fdtd_session* session, int64_t* info);
 
 void b200fdtd_session_destroy(b200fdtd_session* session);
 

@@ -280,3 +280,295 @@ def fdtdz_decomposed(epsilon, dt, source_field, source_waveform, source_position
   if gather:
     run.close()
   return out
+
+
+# ===================================================================================================
+# y-slab decomposition with ghost zones: G time steps per halo exchange, systolic kernel per slab
+# ===================================================================================================
+#
+# The x-slab scheme above exchanges a face every half-step, which ties it to the per-step kernels.
+# Cutting along y instead leaves the x sweep of the persistent systolic kernel intact: every rank
+# owns Y/N columns plus G ghost columns per side, copies its neighbours' edge columns (E, H and
+# the CPML psi arrays) into the ghosts, and then advances G whole steps in ONE launch
+# (``b200fdtd_session_advance``) on its local, periodically wrapped domain.  Wrong data enters
+# only through the wrap at the outer ghost edge and travels one column per step, so after G steps
+# it has consumed exactly the ghost zone: owned cells see the inputs of the single-GPU run and the
+# result is bit-identical.  Cost: (Yo + 2G) / Yo redundant work and one packed exchange per G steps.
+
+
+def local_problem_y(kw, rank, world, ghost):
+  """Engine kwargs of this rank's y-slab (ghost columns included) + snapshot crop."""
+  eps = _np(kw["epsilon"]).astype(np.float32)
+  mask = _np(kw["absorption_mask"]).astype(np.float32)
+  sf = _np(kw["source_field"]).astype(np.float32)
+  Y = mask.shape[2]
+  ox, oy, oz = (int(o) for o in kw["offset"])
+  yy = eps.shape[2]
+  y0, y1 = slab_bounds(Y, world, rank)
+  nloc = y1 - y0
+  G = int(ghost)
+  if nloc < max(G, 1):
+    raise ValueError(f"slab of {nloc} columns is narrower than the ghost zone ({G})")
+  cols = np.arange(y0 - G, y1 + G) % Y                       # global column of each local column
+  eps_y = np.clip(cols - oy, 0, yy - 1)                      # edge replication in y
+  loc = dict(kw)
+  loc["epsilon"] = np.ascontiguousarray(eps[:, :, eps_y])
+  loc["absorption_mask"] = np.ascontiguousarray(mask[:, :, cols])
+  loc["offset"] = (ox, 0, oz)
+  axis = 2 if sf.ndim == 5 else (0 if sf.shape[1] == 1 else 1)
+  wf = _np(kw["source_waveform"]).astype(np.float32)
+  if axis == 0:
+    loc["source_field"] = np.ascontiguousarray(sf[:, :, cols])
+  elif axis == 2:
+    loc["source_field"] = np.ascontiguousarray(sf[:, :, :, cols])
+  else:
+    # y-plane source: channel 0 acts on global column p, channel 1 on p-1.  Both must be
+    # applied wherever they fall inside the local range (ghost cells are recomputed, too); at
+    # the outermost ghost column the wrapped partner lands on the other edge column, which is
+    # already invalid after the first step.
+    p = int(kw["source_position"])
+    hit = np.nonzero(cols == p % Y)[0]
+    hit = [int(h) for h in hit if h >= 1]
+    if len(hit) > 1:
+      # (only when a slab plus its ghosts is wider than the domain, e.g. a single rank)
+      raise NotImplementedError("y-plane source visible twice in one slab (owned column and "
+                                "ghost image): use fewer ghost columns or more ranks")
+    if hit:
+      loc["source_position"] = hit[0]
+    else:
+      loc["source_position"] = 1
+      wf = np.zeros_like(wf)
+    loc["source_field"] = sf
+  loc["source_waveform"] = wf
+  g0, g1 = max(oy, y0), min(oy + yy, y1)
+  crop = None
+  if g1 > g0:
+    crop = (g0 - y0 + G, g1 - y0 + G, g0 - oy, g1 - oy)      # (local lo, local hi, out lo, out hi)
+  return loc, nloc, crop
+
+
+def choose_ghost(kw, world, min_ghost=8):
+  """Ghost width for the y-slab scheme: the smallest multiple of the systolic kernel's stage
+  count >= ``min_ghost`` (a launch of G steps keeps all S pipeline stages busy only if S divides
+  G).  A pure function of the global shapes (widest slab), so every rank picks the same value."""
+  from . import fdtdz_jax as shim
+  mask = kw["absorption_mask"]
+  eps = kw["epsilon"]
+  sf = kw["source_field"]
+  X, Y = int(mask.shape[1]), int(mask.shape[2])
+  nloc = -(-Y // world)
+  axis = 2 if len(sf.shape) == 5 else (0 if sf.shape[1] == 1 else 1)
+  Z = int(np.asarray(kw["pml_kappa"]).shape[0])
+  zero = np.float32(0)
+  G = int(min_ghost)
+  for _ in range(4):
+    Yl = nloc + 2 * G
+    loc = dict(kw)
+    loc["epsilon"] = np.broadcast_to(zero, (3, int(eps.shape[1]), Yl, int(eps.shape[3])))
+    loc["absorption_mask"] = np.broadcast_to(zero, (3, X, Yl))
+    loc["source_field"] = np.broadcast_to(zero, {0: (2, 1, Yl, Z), 1: (2, X, 1, Z),
+                                                 2: (2, 2, X, Yl, 1)}[axis])
+    loc["offset"] = (int(kw["offset"][0]), 0, int(kw["offset"][2]))
+    loc["source_position"] = min(int(kw["source_position"]), (Yl if axis == 1 else 10**9) - 1)
+    info = shim.plan_info(**loc)
+    S = info["stages"] if info["kernel"] == "systolic_lean" else 1
+    G2 = S * max(1, -(-int(min_ghost) // S))
+    if G2 == G:
+      break
+    G = G2
+  return min(G, Y // world)
+
+
+class CudaSlabY:
+  """y-slab engine over the C ABI's stepping session: whole-step ``advance`` (one persistent
+  systolic launch per call when the geometry allows it, per-step kernels otherwise)."""
+
+  def __init__(self, loc, device, kernel="auto"):
+    from . import fdtdz_jax as shim
+    self.shim = shim
+    L = shim.lib()
+    loc = dict(loc)
+    lp = dict(loc.get("launch_params") or {})
+    lp.setdefault("kernel", kernel)
+    loc["launch_params"] = lp
+    self.d = shim.make_desc(**{k: loc[k] for k in (
+        "epsilon", "dt", "source_field", "source_waveform", "source_position", "absorption_mask",
+        "pml_kappa", "pml_sigma", "pml_alpha", "pml_widths", "output_steps",
+        "use_reduced_precision", "launch_params", "offset")})
+    self.device = torch.device(device)
+    names = ("epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa",
+             "pml_sigma", "pml_alpha")
+    self.inputs = [torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
+                   for k in names]
+    L.b200fdtd_session_workspace_bytes.restype = ctypes.c_size_t
+    nbytes = L.b200fdtd_session_workspace_bytes(ctypes.byref(self.d))
+    if nbytes == 0:
+      raise RuntimeError(shim._last_error())
+    self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+    nout = L.b200fdtd_num_outputs(ctypes.byref(self.d))
+    self.out = torch.zeros((nout, 3, self.d.xx, self.d.yy, self.d.zz), dtype=torch.float32,
+                           device=self.device)
+    self.session = ctypes.c_void_p()
+    L.b200fdtd_session_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                          ctypes.c_void_p]
+    L.b200fdtd_session_advance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p]
+    L.b200fdtd_session_layout2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.b200fdtd_session_destroy.argtypes = [ctypes.c_void_p]
+    L.b200fdtd_session_destroy.restype = None
+    self.L = L
+    with torch.cuda.device(self.device):
+      rc = L.b200fdtd_session_create(
+          ctypes.byref(self.d), shim._void_array([t.data_ptr() for t in self.inputs]),
+          shim._void_array([self.out.data_ptr()]), self.ws.data_ptr(), nbytes, self._stream(),
+          ctypes.byref(self.session))
+    if rc != 0:
+      raise RuntimeError(f"b200fdtd_session_create failed ({rc}): {shim._last_error()}")
+    info = (ctypes.c_int64 * 16)()
+    L.b200fdtd_session_layout2(self.session, info)
+    (e_off, h_off, comp_b, plane_b, zp, el, X, Y, e2_off, psi_off, psi_b, psi2_off, psi_k,
+     pingpong, kernel_id, stages) = (int(v) for v in info)
+    self.pingpong, self.stages = bool(pingpong), stages
+    self.kernel = {v: k for k, v in shim._KERNELS.items()}.get(kernel_id, str(kernel_id))
+    dt = torch.float32 if el == 4 else torch.float16
+
+    def fview(off):
+      return self.ws[off:off + 3 * comp_b].view(dt).view(3, X, Y, zp)
+
+    def pview(off):
+      return self.ws[off:off + 2 * psi_b].view(torch.float32).view(2, X, Y, psi_k)
+    psiE = pview(psi_off + 2 * psi_b)
+    self._sets = [[fview(e_off), fview(h_off), pview(psi_off), psiE]]
+    if self.pingpong:
+      self._sets.append([fview(e2_off), fview(e2_off + (h_off - e_off)), pview(psi2_off), psiE])
+
+  def _stream(self):
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def state(self, n):
+    """[E, H, psiH, psiE] views (C, X, Y, .) holding the state after ``n`` steps."""
+    return self._sets[n & 1] if self.pingpong else self._sets[0]
+
+  def advance(self, n0, nsteps):
+    rc = self.L.b200fdtd_session_advance(self.session, int(n0), int(nsteps), self._stream())
+    if rc:
+      raise RuntimeError(self.shim._last_error())
+
+  def snapshots(self):
+    return self.out
+
+  def close(self):
+    if self.session:
+      torch.cuda.synchronize(self.device)
+      self.L.b200fdtd_session_destroy(self.session)
+      self.session = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+def _pack(state, lo, hi):
+  """Columns [lo, hi) of every state array, as one contiguous byte buffer."""
+  return torch.cat([t[:, :, lo:hi].reshape(-1).view(torch.uint8) for t in state])
+
+
+def _unpack(buf, state, lo, hi):
+  off = 0
+  for t in state:
+    dst = t[:, :, lo:hi]
+    n = dst.numel() * dst.element_size()
+    dst.copy_(buf[off:off + n].view(dst.dtype).view(dst.shape))
+    off += n
+
+
+class YSlabRun:
+  """One y-decomposed engine call: set-up in ``__init__``, the time loop in ``run``."""
+
+  def __init__(self, kw, ghost=8, group=None, make_slab=None, device=None, kernel="auto",
+               local=None):
+    """``local`` = a pre-built ``(local kwargs, nloc, crop)`` triple (what ``local_problem_y``
+    returns) for domains whose global arrays are too large to materialise on every rank."""
+    self.kw, self.group = kw, group
+    self.world, self.rank = 1, 0
+    if dist.is_available() and dist.is_initialized():
+      self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    self.G = choose_ghost(kw, self.world) if ghost is None else int(ghost)
+    loc, self.nloc, self.crop = (local if local is not None else
+                                 local_problem_y(kw, self.rank, self.world, self.G))
+    if make_slab is None:
+      if not torch.cuda.is_available():
+        raise RuntimeError("fdtdz_decomposed_y needs a CUDA device (no CPU fallback)")
+      dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+      self.slab = CudaSlabY(loc, dev, kernel)
+    else:
+      self.slab = make_slab(loc)
+    self.tt = _np(kw["source_waveform"]).shape[0]
+
+  def _peer(self, r):
+    r %= self.world
+    if self.group is not None and self.world > 1:
+      return dist.get_global_rank(self.group, r)
+    return r
+
+  def run(self):
+    slab, G, group, world = self.slab, self.G, self.group, self.world
+    right, left = self._peer(self.rank + 1), self._peer(self.rank - 1)
+    Yl = self.nloc + 2 * G
+    for n0 in range(0, self.tt, max(G, 1)):
+      st = slab.state(n0)
+      if n0 > 0:                                             # (the initial state is all zero)
+        send_lo = _pack(st, G, 2 * G)                        # my low owned edge
+        send_hi = _pack(st, Yl - 2 * G, Yl - G)              # my high owned edge
+        recv_hi, recv_lo = torch.empty_like(send_lo), torch.empty_like(send_hi)
+        _exchange(send_lo, recv_hi, left, right, group, world)   # -> left's high ghost
+        _exchange(send_hi, recv_lo, right, left, group, world)   # -> right's low ghost
+        _unpack(recv_hi, st, Yl - G, Yl)
+        _unpack(recv_lo, st, 0, G)
+      slab.advance(n0, min(G, self.tt - n0))
+
+  def local_snapshots(self):
+    snaps = self.slab.snapshots()                            # (n_out, 3, xx, nloc+2G, zz)
+    if not isinstance(snaps, torch.Tensor):
+      snaps = torch.from_numpy(np.ascontiguousarray(snaps))
+    if self.crop is None:
+      return 0, 0, snaps[:, :, :, :0]
+    return self.crop[2], self.crop[3], snaps[:, :, :, self.crop[0]:self.crop[1]]
+
+  def gathered_snapshots(self):
+    lo, hi, snaps = self.local_snapshots()
+    shape = tuple(self.kw["epsilon"].shape)
+    full = torch.zeros((snaps.shape[0], 3) + shape[1:], dtype=torch.float32, device=snaps.device)
+    if hi > lo:
+      full[:, :, :, lo:hi] = snaps
+    if self.world > 1:
+      dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+    return full
+
+  def close(self):
+    if hasattr(self.slab, "close"):
+      self.slab.close()
+
+
+def fdtdz_decomposed_y(epsilon, dt, source_field, source_waveform, source_position,
+                       absorption_mask, pml_kappa, pml_sigma, pml_alpha, pml_widths,
+                       output_steps, use_reduced_precision, launch_params=None, offset=(0, 0, 0),
+                       *, ghost=8, group=None, make_slab=None, device=None, gather=True):
+  """The engine call, y-decomposed with ``ghost`` ghost columns per side over the ranks of
+  ``group``: ``ghost`` time steps per halo exchange (``None``: the smallest multiple of the
+  kernel's pipeline depth >= 8).  Same contract as ``fdtdz_decomposed``."""
+  kw = dict(epsilon=epsilon, dt=dt, source_field=source_field, source_waveform=source_waveform,
+            source_position=source_position, absorption_mask=absorption_mask,
+            pml_kappa=pml_kappa, pml_sigma=pml_sigma, pml_alpha=pml_alpha,
+            pml_widths=pml_widths, output_steps=output_steps,
+            use_reduced_precision=use_reduced_precision, launch_params=launch_params,
+            offset=offset)
+  run = YSlabRun(kw, ghost=ghost, group=group, make_slab=make_slab, device=device)
+  run.run()
+  out = run.gathered_snapshots() if gather else run.local_snapshots()
+  if gather:
+    run.close()
+  return out

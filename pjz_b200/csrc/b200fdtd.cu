@@ -97,6 +97,7 @@ static Geom make_geom(const b200fdtd_desc* d) {
   g.src_axis = d->source_axis; g.src_pos = d->source_position;
   g.out_start = d->out_start; g.out_stop = d->out_stop; g.out_step = d->out_step;
   g.tt = d->tt;
+  g.n0 = 0;
   g.dt = d->dt;
   g.P = (long long)g.Y * g.Zp;
   g.N = (long long)g.X * g.P;
@@ -568,6 +569,8 @@ struct b200fdtd_session {
   b200fdtd_desc d;
   Geom g;
   Workspace w;
+  Plan plan;
+  bool systolic;        // persistent-launch kernel (lean): ping-pong state, advance() only
   char* ws;
   bool reduced;
   Ptrs<float> pf;
@@ -575,10 +578,35 @@ struct b200fdtd_session {
   dim3 grid;
 };
 
+// Sessions use the warp-per-column-pair systolic kernel when the plan selects it (fp32, 32
+// z-vectors) and the per-step kernels otherwise.
+static int session_plan(const b200fdtd_desc* desc, const Geom& g, Plan* plan, bool* systolic) {
+  *systolic = false;
+  plan->kernel = B200FDTD_KERNEL_TWOPASS;
+  plan->depth = 0;
+  if (desc->kernel == B200FDTD_KERNEL_TWOPASS) return B200FDTD_OK;
+  Plan p;
+  int rc = make_plan(desc, g, &p);
+  if (rc) {
+    if (desc->kernel == B200FDTD_KERNEL_AUTO) return B200FDTD_OK;
+    return rc;
+  }
+  if (p.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
+    *plan = p;
+    *systolic = true;
+  } else if (desc->kernel != B200FDTD_KERNEL_AUTO) {
+    return fail(B200FDTD_EUNSUPPORTED, "sessions support the twopass and systolic_lean kernels");
+  }
+  return B200FDTD_OK;
+}
+
 size_t b200fdtd_session_workspace_bytes(const b200fdtd_desc* desc) {
   if (validate(desc)) return 0;
   const Geom g = make_geom(desc);
-  return carve(g, desc->use_reduced_precision != 0, false, nullptr).total;
+  Plan plan;
+  bool systolic;
+  if (session_plan(desc, g, &plan, &systolic)) return 0;
+  return carve(g, desc->use_reduced_precision != 0, systolic, &plan.sys).total;
 }
 
 int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs,
@@ -592,8 +620,12 @@ int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs
     if (!inputs[i]) return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i);
   if (num_outputs(desc) > 0 && !outputs[0]) return fail(B200FDTD_EINVAL, "outputs[0] is NULL");
   const Geom g = make_geom(desc);
-  if (g.X > 65535) return fail(B200FDTD_EUNSUPPORTED, "sessions support X <= 65535");
-  const Workspace w = carve(g, desc->use_reduced_precision != 0, false, nullptr);
+  Plan plan;
+  bool systolic;
+  rc = session_plan(desc, g, &plan, &systolic);
+  if (rc) return rc;
+  if (!systolic && g.X > 65535) return fail(B200FDTD_EUNSUPPORTED, "per-step sessions support X <= 65535");
+  const Workspace w = carve(g, desc->use_reduced_precision != 0, systolic, &plan.sys);
   if (workspace_bytes < w.total)
     return fail(B200FDTD_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total,
                 workspace_bytes);
@@ -601,6 +633,7 @@ int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs
   b200fdtd_session* s = new (std::nothrow) b200fdtd_session();
   if (!s) return fail(B200FDTD_EINVAL, "out of host memory");
   s->d = *desc; s->g = g; s->w = w; s->ws = static_cast<char*>(workspace);
+  s->plan = plan; s->systolic = systolic;
   s->reduced = desc->use_reduced_precision != 0;
   s->grid = dim3((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads, g.X);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -613,6 +646,7 @@ int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs
 
 int b200fdtd_session_step_h(b200fdtd_session* s, void* stream) {
   if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (s->systolic) return fail(B200FDTD_EUNSUPPORTED, "systolic sessions advance whole steps");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (s->reduced) twopass_h_kernel<__half><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->ph);
   else twopass_h_kernel<float><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->pf);
@@ -622,11 +656,39 @@ int b200fdtd_session_step_h(b200fdtd_session* s, void* stream) {
 
 int b200fdtd_session_step_e(b200fdtd_session* s, int n, void* stream) {
   if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (s->systolic) return fail(B200FDTD_EUNSUPPORTED, "systolic sessions advance whole steps");
   if (n < 0 || n >= s->g.tt) return fail(B200FDTD_EINVAL, "step %d outside [0,%d)", n, s->g.tt);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (s->reduced) twopass_e_kernel<__half><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->ph, n);
   else twopass_e_kernel<float><<<s->grid, kTwoPassThreads, 0, st>>>(s->g, s->pf, n);
   CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stream) {
+  if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (n0 < 0 || nsteps < 0 || n0 + nsteps > s->d.tt)
+    return fail(B200FDTD_EINVAL, "steps [%d,%d) outside [0,%d)", n0, n0 + nsteps, s->d.tt);
+  if (nsteps == 0) return B200FDTD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!s->systolic) {
+    for (int n = n0; n < n0 + nsteps; ++n) {
+      int rc = b200fdtd_session_step_h(s, stream);
+      if (rc) return rc;
+      rc = b200fdtd_session_step_e(s, n, stream);
+      if (rc) return rc;
+    }
+    return B200FDTD_OK;
+  }
+  // One persistent launch over steps [n0, n0+nsteps): the state of step n lives in buffer set
+  // n & 1, so consecutive calls chain without copies.  Progress counters restart at zero.
+  Geom g = s->g;
+  g.n0 = n0;
+  g.tt = n0 + nsteps;
+  CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
+  const int rc = lean_launch(g, s->pf, s->plan.sys, reinterpret_cast<unsigned*>(s->ws + s->w.sync), st);
+  if (rc != 0)
+    return fail(B200FDTD_ECUDA, "systolic launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return B200FDTD_OK;
 }
 
@@ -641,6 +703,22 @@ int b200fdtd_session_layout(const b200fdtd_session* s, int64_t* info) {
   info[5] = el;                                   // bytes per element (4 fp32, 2 fp16 storage)
   info[6] = s->g.X;
   info[7] = s->g.Y;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_layout2(const b200fdtd_session* s, int64_t* info) {
+  int rc = b200fdtd_session_layout(s, info);
+  if (rc) return rc;
+  const int64_t VW = s->reduced ? 8 : 4;
+  const int64_t psi_bytes = (int64_t)s->g.X * s->g.Y * s->g.npg * VW * 4;
+  info[8] = s->systolic ? (int64_t)s->w.fields2 : -1;   // Ex of buffer set 1 (Hx follows as in set 0)
+  info[9] = (int64_t)s->w.psi;                    // psiH[0] of set 0; then psiH[1], psiE[0], psiE[1]
+  info[10] = psi_bytes;                           // bytes per psi array
+  info[11] = s->systolic ? (int64_t)s->w.psi + 4 * psi_bytes : -1;   // psiH[0] of set 1, then psiH[1]
+  info[12] = (int64_t)s->g.npg * VW;              // psi floats per (x, y) column
+  info[13] = s->systolic ? 1 : 0;                 // 1: state of step n lives in set n & 1
+  info[14] = s->plan.kernel;
+  info[15] = s->systolic ? s->plan.sys.stages : 0;
   return B200FDTD_OK;
 }
 

@@ -22,7 +22,8 @@ struct Geom {
   int ox, oy, oz;      // ... and its offset
   int src_axis, src_pos;
   int out_start, out_stop, out_step;
-  int tt;
+  int tt;              // one past the last step of this launch
+  int n0;              // first step of this launch (stepping sessions; 0 for a whole run)
   float dt;
   long long P;         // elements per x-plane   = Y * Zp
   long long N;         // elements per component = X * P

@@ -138,13 +138,13 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         if (pf_done < front + 1u) pf_done = front + 1u;
         for (; pf_done < want; ++pf_done) {
           const unsigned sweep = pf_done / sweep_iters, it = pf_done % sweep_iters;
-          const int n = j + (int)sweep * S;
+          const int n = g.n0 + j + (int)sweep * S;
           if (n >= g.tt) break;
           // Only planes the previous step has already produced: prefetching a plane that is
           // about to be overwritten would fetch dead data from HBM.  (A follower finds them in
           // L2 anyway; the prefetch matters for the stage that leads the window.)
-          if (n > 0) {
-            const unsigned m = (unsigned)(n / S);
+          if (n > g.n0) {
+            const unsigned m = (unsigned)((n - g.n0) / S);
             const unsigned need = (j > 0 ? m : m - 1u) * (unsigned)X + (unsigned)min((int)it + 2, X);
             if (min(v0, min(v1, v2)) < need) break;
           }
@@ -236,11 +236,11 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     }
   };
 
-  for (int n = j; n < g.tt && ok; n += S) {
-    const int m = n / S;
+  for (int n = g.n0 + j; n < g.tt && ok; n += S) {
+    const int m = (n - g.n0) / S;
     const unsigned base_prev = (unsigned)((j > 0 ? m : m - 1)) * (unsigned)X;
     const unsigned base_mine = (unsigned)m * (unsigned)X;
-    const bool has_prev = n > 0, has_next = n + 1 < g.tt && j + 1 < S;
+    const bool has_prev = n > g.n0, has_next = n + 1 < g.tt && j + 1 < S;
     const int rb = n & 1, wb = rb ^ 1;
     const int cstart = n % X;
     const int oi = snapshot_index(g, n);

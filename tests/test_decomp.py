@@ -56,6 +56,22 @@ class OracleSlab:
     return self.out
 
 
+class OracleSlabY(OracleSlab):
+  """y-slab engine (whole-step ``advance``) backed by the float64 NumPy spec (tests only)."""
+
+  def __init__(self, loc):
+    super().__init__(loc)
+    self._state = [self.E, self.H, torch.from_numpy(self.st.psiH), torch.from_numpy(self.st.psiE)]
+
+  def state(self, n):
+    return self._state
+
+  def advance(self, n0, nsteps):
+    for n in range(n0, n0 + nsteps):
+      self.step_h()
+      self.step_e(n)
+
+
 def _problems():
   from tests.problems import random_problem
   return [
@@ -79,6 +95,80 @@ def _worker(rank, world, port, out_path):
     np.savez(out_path, *outs)
   dist.barrier()
   dist.destroy_process_group()
+
+
+def _problems_y():
+  from tests.problems import random_problem
+  return [
+      random_problem(domain=(9, 24, 8), axis=0, pml=(2, 3), tt=14, seed=31, output_steps=(5, 14, 4)),
+      random_problem(domain=(8, 21, 8), axis=1, pml=(2, 2), tt=13, seed=32, output_steps=(3, 13, 3),
+                     src_pos=10),                # y-plane 10 / 9 straddle the 2-rank cut (10|11)
+      random_problem(domain=(7, 18, 12), axis=2, pml=(3, 3), tt=12, seed=33, output_steps=(11, 12, 1)),
+      random_problem(domain=(6, 20, 8), axis=1, pml=(0, 3), tt=9, seed=34, output_steps=(0, 9, 4),
+                     src_pos=0),
+  ]
+
+
+def _worker_y(rank, world, port, out_path, ghost):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from pjz_b200._decomp import fdtdz_decomposed_y
+  outs = [fdtdz_decomposed_y(**kw, ghost=ghost, make_slab=OracleSlabY).numpy()
+          for kw in _problems_y()]
+  if rank == 0:
+    np.savez(out_path, *outs)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ghost", [(2, 3), (3, 2), (2, 5)])
+def test_y_decomposed_oracle_matches_single_domain(world, ghost, tmp_path):
+  """Ghost-zone scheme: `ghost` steps per exchange, E/H/psi columns, all source orientations."""
+  from oracle import fdtd_numpy
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "ddy.npz")
+  mp.spawn(_worker_y, args=(world, port, out, ghost), nprocs=world, join=True)
+  got = np.load(out)
+  for i, kw in enumerate(_problems_y()):
+    np.testing.assert_array_equal(got[f"arr_{i}"], fdtd_numpy.fdtdz(**kw))
+
+
+def test_y_single_rank_wraps_onto_itself():
+  from oracle import fdtd_numpy
+  from pjz_b200._decomp import fdtdz_decomposed_y
+  for kw in _problems_y()[:3]:
+    for ghost in (1, 4):
+      out = fdtdz_decomposed_y(**kw, ghost=ghost, make_slab=OracleSlabY).numpy()
+      np.testing.assert_array_equal(out, fdtd_numpy.fdtdz(**kw))
+  with pytest.raises(NotImplementedError):       # y-plane source at column 0: owned + ghost image
+    fdtdz_decomposed_y(**_problems_y()[3], ghost=2, make_slab=OracleSlabY)
+
+
+def test_y_slab_inputs():
+  from pjz_b200._decomp import local_problem_y
+  from tests.problems import random_problem
+  kw = random_problem(domain=(6, 12, 8), sub=(4, 5, 3), offset=(1, 4, 2), axis=1, tt=6, seed=1,
+                      src_pos=7)
+  loc, nloc, crop = local_problem_y(kw, 1, 2, 2)   # owns columns 6..11, ghosts 4,5 and 0,1
+  assert nloc == 6 and loc["epsilon"].shape == (3, 4, 10, 3) and loc["offset"] == (1, 0, 2)
+  assert loc["absorption_mask"].shape == (3, 6, 10)
+  np.testing.assert_array_equal(loc["absorption_mask"][:, :, 0], kw["absorption_mask"][:, :, 4])
+  np.testing.assert_array_equal(loc["absorption_mask"][:, :, 9], kw["absorption_mask"][:, :, 1])
+  # epsilon columns: global 4..8 are the sub-volume; beyond it the edge is replicated
+  np.testing.assert_array_equal(loc["epsilon"][:, :, 0], kw["epsilon"][:, :, 0])
+  np.testing.assert_array_equal(loc["epsilon"][:, :, 9], kw["epsilon"][:, :, 0])   # global col 1
+  np.testing.assert_array_equal(loc["epsilon"][:, :, 5], kw["epsilon"][:, :, 4])   # global col 9
+  assert loc["source_position"] == 3 and loc["source_waveform"].any()              # global 7
+  assert crop == (2, 5, 2, 5)                      # global 6..8 -> local 2..4, out 2..4
+  loc0, _, crop0 = local_problem_y(kw, 0, 2, 2)    # owns 0..5; ghosts 10,11 and 6,7: source in ghost
+  assert loc0["source_position"] == 9 and loc0["source_waveform"].any()
+  assert crop0 == (6, 8, 0, 2)
+  with pytest.raises(ValueError):
+    local_problem_y(kw, 0, 4, 4)
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -141,6 +231,61 @@ def test_session_driver_equals_one_call_engine(built):
     want = fdtdz_jax.fdtdz(**dev).cpu().numpy()
     got = fdtdz_decomposed(**kw).cpu().numpy()   # world = 1: the slab wraps onto itself
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_y_session_driver_equals_one_call_engine(built):
+  """World 1 (the slab wraps onto itself through its own ghosts): the systolic stepping session
+  (lean geometry) and the per-step session (any geometry) both reproduce the one-call engine."""
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import YSlabRun, fdtdz_decomposed_y
+  from tests.problems import random_problem
+  cases = [((10, 40, 128), (16, 16), 0, 6, False), ((9, 36, 128), (4, 6), 1, 4, False),
+           ((8, 30, 126), (0, 0), 2, 7, False), ((12, 20, 40), (5, 6), 0, 3, False),
+           ((10, 24, 32), (4, 4), 1, 2, True)]
+  for domain, pml, axis, ghost, reduced in cases:
+    kw = random_problem(domain=domain, axis=axis, pml=pml, tt=27, seed=80 + axis,
+                        output_steps=(9, 27, 5), reduced=reduced)
+    dev = dict(kw)
+    dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+    want = fdtdz_jax.fdtdz(**dev).cpu().numpy()
+    got = fdtdz_decomposed_y(**kw, ghost=ghost).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+  run = YSlabRun(random_problem(domain=(10, 40, 128), pml=(16, 16), tt=8, seed=1), ghost=4)
+  assert run.slab.kernel == "systolic_lean" and run.slab.pingpong
+  run.close()
+
+
+def _gpu_worker_y(rank, world, port, out_path):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  from pjz_b200._decomp import fdtdz_decomposed_y
+  from tests.problems import random_problem
+  kw = random_problem(domain=(24, 64, 128), axis=1, pml=(16, 16), tt=40, seed=78,
+                      output_steps=(20, 40, 6), src_pos=31)
+  out = fdtdz_decomposed_y(**kw, ghost=6).cpu().numpy()
+  if rank == 0:
+    np.save(out_path, out)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_y_decomposition_is_bit_exact(built, tmp_path):
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs")
+  from oracle import fdtd_c
+  from tests.problems import random_problem
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "ddy.npy")
+  mp.spawn(_gpu_worker_y, args=(2, port, out), nprocs=2, join=True)
+  kw = random_problem(domain=(24, 64, 128), axis=1, pml=(16, 16), tt=40, seed=78,
+                      output_steps=(20, 40, 6), src_pos=31)
+  np.testing.assert_array_equal(np.load(out), fdtd_c.fdtdz(**kw))
 
 
 def _gpu_worker(rank, world, port, out_path):
