@@ -63,7 +63,9 @@ enum {
   B200FDTD_IN_PML_KAPPA = 4,
   B200FDTD_IN_PML_SIGMA = 5,
   B200FDTD_IN_PML_ALPHA = 6,
-  B200FDTD_NUM_INPUTS = 7
+  B200FDTD_NUM_INPUTS = 7,      /* mandatory inputs                                          */
+  B200FDTD_IN_PROJECTION = 7,   /* optional 8th input, read only when desc->proj_rows > 0     */
+  B200FDTD_MAX_INPUTS = 8
 };
 
 /* Kernel selection (launch_params). */
@@ -102,7 +104,13 @@ typedef struct b200fdtd_desc {
   int32_t threads;              /* CTA size override                                        */
   int32_t prefetch;             /* systolic_async: planes of prefetch distance (1..3)       */
   int32_t cols;                 /* systolic_async: columns per compute thread (1 | 2)       */
-  int32_t reserved[2];
+  /* Fused frequency projection (replaces the snapshot dump + pinv einsum of
+   * /root/reference/src/pjz/_field.py:272-279).  proj_rows = R > 0: inputs[7] is a (R, n_out)
+   * float32 matrix W and the output is (R, 3, xx, yy, zz) with
+   *   out[r] = sum_s W[r][s] * snapshot_s   (accumulated in snapshot order with one fmaf each),
+   * formed inside the time-stepping kernels; no snapshot is ever written.  0: snapshots. */
+  int32_t proj_rows;
+  int32_t reserved;
 } b200fdtd_desc;
 
 /* ABI version of the loaded library. */
@@ -117,7 +125,8 @@ int b200fdtd_validate(const b200fdtd_desc* desc);
 /* Number of snapshots len(range(out_start, out_stop, out_step)); < 0 on invalid desc. */
 int b200fdtd_num_outputs(const b200fdtd_desc* desc);
 
-/* Bytes of the output array (n_out, 3, xx, yy, zz) float32; 0 on invalid desc. */
+/* Bytes of the output array, float32 (n_out, 3, xx, yy, zz) -- or (proj_rows, 3, xx, yy, zz)
+ * with the fused projection; 0 on invalid desc. */
 size_t b200fdtd_output_bytes(const b200fdtd_desc* desc);
 
 /* Scratch bytes b200fdtd_run needs in device memory; 0 on invalid desc. */
@@ -148,6 +157,18 @@ void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
  * `desc` on the current device: {kernel, tile_y, stages, threads, ctas, smem_bytes,
  * launches_per_run, l2_window_bytes>>20}.  */
 int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info);
+
+
+/* ---- Adjoint product-reduce -----------------------------------------------------------------------
+ * The gradient of pjz.scatter's custom_vjp in one pass (replaces the N^2 full-volume temporaries
+ * grads[i][j] = F_i F_j / a_i of /root/reference/src/pjz/_field.py:380-382 and their reduction
+ * against the cotangents, :393-398):
+ *     out[v] = sum_{i,j < nports} sum_{w < ww} Re( coef[i][j][w] * F_i[w][v] * F_j[w][v] )
+ * fields[i] : device pointer to port i's phasor field, complex64 (ww, nvox), nvox = 3*xx*yy*zz
+ * coef      : device complex64 (nports, nports, ww)  (= conj(cotangent_ij) / amplitude_i)
+ * out       : device float32 (nvox).   nports <= 16, ww <= 64.  Asynchronous on `stream`. */
+int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* fields,
+                            const void* coef, void* out, void* stream);
 
 
 /* ---- Stepping sessions ---------------------------------------------------------------------------

@@ -222,3 +222,20 @@ int oracle_fdtd_max_threads(void) {
   return 1;
 #endif
 }
+
+
+/* Fused frequency projection (engine extension, include/b200fdtd.h `proj_rows`): out[r] =
+ * sum_s w[r][s] * snaps[s], accumulated from zero in snapshot order with one fmaf per term --
+ * the order the CUDA kernels use when they accumulate in place at each output step.
+ * (Restates the pinv einsum of /root/reference/src/pjz/_field.py:276-277 as a running sum.) */
+void oracle_fdtd_project(const float* snaps, const float* w, int rows, int nout, size_t n,
+                         float* out) {
+  for (int r = 0; r < rows; ++r) {
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)n; ++i) {
+      float acc = 0.f;
+      for (int s = 0; s < nout; ++s) acc = fmaf(w[(size_t)r * nout + s], snaps[(size_t)s * n + i], acc);
+      out[(size_t)r * n + i] = acc;
+    }
+  }
+}

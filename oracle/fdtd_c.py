@@ -60,7 +60,7 @@ def max_threads():
 def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
           pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
           use_reduced_precision=False, launch_params=None, offset=(0, 0, 0),
-          nthreads=0, steps_override=-1, want_output=True):
+          nthreads=0, steps_override=-1, want_output=True, output_projection=None):
   eps, sf, wf = _f32(epsilon), _f32(source_field), _f32(source_waveform)
   mask, kap, sig, alp = (_f32(a) for a in (absorption_mask, pml_kappa, pml_sigma, pml_alpha))
   X, Y, Z = domain_shape(mask, kap)
@@ -86,4 +86,13 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
                              ctypes.c_int(nthreads), ctypes.c_int(steps_override))
   if rc != 0:
     raise ValueError(f"oracle_fdtd_run failed with code {rc}")
+  if output_projection is not None and out is not None:
+    w = _f32(output_projection)
+    if w.ndim != 2 or w.shape[1] != nout:
+      raise ValueError(f"output_projection must have shape (rows, {nout}), got {w.shape}")
+    proj = np.zeros((w.shape[0],) + out.shape[1:], np.float32)
+    n = int(np.prod(out.shape[1:]))
+    lib().oracle_fdtd_project(_ptr(out), _ptr(w), ctypes.c_int(w.shape[0]), ctypes.c_int(nout),
+                              ctypes.c_size_t(n), _ptr(proj))
+    return proj
   return out

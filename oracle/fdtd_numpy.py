@@ -203,7 +203,7 @@ class State:
 def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
           pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
           use_reduced_precision=False, launch_params=None, offset=(0, 0, 0),
-          dtype=np.float64, return_state=False):
+          dtype=np.float64, return_state=False, output_projection=None):
   """Oracle with the ``fdtdz_jax.fdtdz`` keyword signature (/root/reference/src/pjz/_field.py:254-269).
 
   Returns float32 ``(n_out, 3, xx, yy, zz)``.  ``dtype`` selects the arithmetic precision of
@@ -236,6 +236,10 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
     if oi < len(outs) and n == outs[oi]:
       out[oi] = st.E[:, ox:ox + xx, oy:oy + yy, oz:oz + zz]
       oi += 1
+  if output_projection is not None:
+    # engine extension: out[r] = sum_s W[r, s] * snapshot_s  (cf. _field.py:276-277)
+    w = np.asarray(output_projection, np.float32).astype(np.float64)
+    out = np.einsum("rs,s...->r...", w, out.astype(np.float64)).astype(np.float32)
   if return_state:
     return out, st
   return out

@@ -263,7 +263,8 @@ def project_snapshots(fields, omega, output_steps, dt):
   return torch.complex(outputs[:ww], outputs[ww:])
 
 
-def field(epsilon, source, omega, source_pos, sim_params, *, engine=None):
+def field(epsilon, source, omega, source_pos, sim_params, *, engine=None,
+          fuse_projection=False):
   """Time-harmonic solution of Maxwell's equations; mirror of ``pjz.field``
   (/root/reference/src/pjz/_field.py:171-279).
 
@@ -274,12 +275,21 @@ def field(epsilon, source, omega, source_pos, sim_params, *, engine=None):
     source_pos: source plane index along the propagation axis.
     sim_params: ``SimParams``.
     engine: callable with the ``fdtdz_jax.fdtdz`` signature; default = the CUDA engine.
+    fuse_projection: form the phasors inside the time-stepping kernels (the engine's
+      ``output_projection`` extension) instead of dumping 2ww+1 snapshots and projecting them
+      afterwards (:272-279); same pinv weights, applied as a running sum.
 
   Returns:
     ``(ww, 3, xx, yy, zz)`` complex64 torch tensor.
   """
   engine = engine or _default_engine()
   kwargs, omega_np, output_steps = engine_inputs(epsilon, source, omega, source_pos, sim_params)
+  if fuse_projection:
+    ww = omega_np.shape[0]
+    pinv = np.linalg.pinv(_output_phases(omega_np, output_steps, sim_params.dt).T)
+    out = _as_tensor(engine(**kwargs, output_projection=pinv.astype(np.float32)),
+                     dtype=torch.float32)
+    return torch.complex(out[:ww], out[ww:])
   fields = engine(**kwargs)
   return project_snapshots(fields, omega_np, output_steps, sim_params.dt)
 
@@ -316,7 +326,7 @@ def _overlap(mode, beta, pos, is_fwd, output):
 
 
 def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=None,
-                  group=None, want_grads=True):
+                  group=None, want_grads=True, fuse_projection=False):
   """Mirror of ``_scatter_impl`` (:346-384).  One independent engine run per port; with a
   ``torch.distributed`` process group the ports are dealt round-robin to the ranks (the
   batch axis of SURVEY.md 8(e)) and the phasor fields are all-gathered afterwards."""
@@ -330,7 +340,8 @@ def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=
   local = {}
   for i in mine:
     m = _as_tensor(modes[i], epsilon.device)
-    local[i] = field(epsilon, torch.mean(m, dim=0), omega, pos[i], sim_params, engine=engine)
+    local[i] = field(epsilon, torch.mean(m, dim=0), omega, pos[i], sim_params, engine=engine,
+                     fuse_projection=fuse_projection)
   if world > 1:
     fields = []
     for i in range(nports):
@@ -361,7 +372,16 @@ def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=
   if want_grads:
     grads = [[fi * fj / a[:, None, None, None, None] for fj in fields]
              for a, fi in zip(amplitudes, fields)]
-  return svals, grads, fields
+  return svals, grads, fields, amplitudes
+
+
+def _scatter_bwd_fused(fields, amplitudes, g):
+  """``_scatter_bwd`` without the N^2 volume temporaries: one CUDA pass over the N phasor fields
+  (``b200fdtd_adjoint_reduce``).  ``g[i][j]`` = conj(cotangent), ``(ww,)``."""
+  from . import fdtdz_jax
+  n = len(fields)
+  coef = torch.stack([torch.stack([g[i][j] / amplitudes[i] for j in range(n)]) for i in range(n)])
+  return fdtdz_jax.adjoint_reduce(fields, coef)
 
 
 def _scatter_bwd(grad, g):
@@ -378,24 +398,31 @@ class _Scatter(torch.autograd.Function):
   """``custom_vjp`` of pjz.scatter (:403-442) as a torch autograd function."""
 
   @staticmethod
-  def forward(ctx, epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine, group):
-    svals, grads, _ = _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params,
-                                    engine, group, want_grads=True)
-    ctx.grads = grads
+  def forward(ctx, epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine, group,
+              fuse_projection):
+    # On the GPU the backward pass is the fused product-reduce kernel over the saved phasor
+    # fields; the N^2 ``grads`` volumes of the reference are only formed on the CPU test path.
+    on_gpu = isinstance(epsilon, torch.Tensor) and epsilon.is_cuda
+    svals, grads, fields, amplitudes = _scatter_impl(
+        epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine, group,
+        want_grads=not on_gpu, fuse_projection=fuse_projection)
+    ctx.grads, ctx.fields, ctx.amplitudes = grads, fields, amplitudes
     ctx.n = len(modes)
     return tuple(s for row in svals for s in row)
 
   @staticmethod
   def backward(ctx, *g):
     n = ctx.n
-    gm = [[torch.conj(g[i * n + j]) if g[i * n + j] is not None else
-           torch.zeros_like(ctx.grads[i][j][:, 0, 0, 0, 0]) for j in range(n)]
+    zero = torch.zeros_like(ctx.amplitudes[0])
+    gm = [[torch.conj(g[i * n + j]) if g[i * n + j] is not None else zero for j in range(n)]
           for i in range(n)]
-    return (_scatter_bwd(ctx.grads, gm),) + (None,) * 8
+    if ctx.grads is None:
+      return (_scatter_bwd_fused(ctx.fields, ctx.amplitudes, gm),) + (None,) * 9
+    return (_scatter_bwd(ctx.grads, gm),) + (None,) * 9
 
 
 def scatter(epsilon, omega, modes, betas, pos, is_fwd, sim_params, *, engine=None,
-            group=None):
+            group=None, fuse_projection=False):
   """Scattering values between ``modes``; mirror of ``pjz.scatter``
   (/root/reference/src/pjz/_field.py:403-442).  Returns ``svals[i][j]`` nested lists of
   ``(ww,)`` complex tensors; differentiable w.r.t. ``epsilon`` when it requires grad (the
@@ -404,8 +431,9 @@ def scatter(epsilon, omega, modes, betas, pos, is_fwd, sim_params, *, engine=Non
   eps_t = _as_tensor(epsilon, dtype=torch.float32)
   n = len(modes)
   if eps_t.requires_grad:
-    flat = _Scatter.apply(eps_t, omega, modes, betas, pos, is_fwd, sim_params, engine, group)
+    flat = _Scatter.apply(eps_t, omega, modes, betas, pos, is_fwd, sim_params, engine, group,
+                          fuse_projection)
     return [[flat[i * n + j] for j in range(n)] for i in range(n)]
-  svals, _, _ = _scatter_impl(eps_t, omega, modes, betas, pos, is_fwd, sim_params, engine,
-                              group, want_grads=False)
+  svals, _, _, _ = _scatter_impl(eps_t, omega, modes, betas, pos, is_fwd, sim_params, engine,
+                                 group, want_grads=False, fuse_projection=fuse_projection)
   return svals

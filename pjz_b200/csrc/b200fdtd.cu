@@ -22,6 +22,7 @@
 #include "kernels_systolic3.cuh"
 #include "kernels_lean.cuh"
 #include "kernels_twopass.cuh"
+#include "postproc.cuh"
 
 namespace b200 {
 
@@ -74,6 +75,10 @@ static int validate(const b200fdtd_desc* d) {
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
   if (d->kernel < 0 || d->kernel > 5) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
   if (d->cols < 0 || d->cols > 2) return fail(B200FDTD_EINVAL, "cols must be 0, 1 or 2");
+  if (d->proj_rows < 0 || d->proj_rows > 64)
+    return fail(B200FDTD_EINVAL, "proj_rows must be in [0, 64], got %d", d->proj_rows);
+  if (d->proj_rows > 0 && d->out_stop <= d->out_start)
+    return fail(B200FDTD_EINVAL, "fused projection needs at least one output step");
   return B200FDTD_OK;
 }
 
@@ -96,6 +101,8 @@ static Geom make_geom(const b200fdtd_desc* d) {
   g.ox = d->off_x; g.oy = d->off_y; g.oz = d->off_z;
   g.src_axis = d->source_axis; g.src_pos = d->source_position;
   g.out_start = d->out_start; g.out_stop = d->out_stop; g.out_step = d->out_step;
+  g.proj_rows = d->proj_rows;
+  g.n_out = num_outputs(d);
   g.tt = d->tt;
   g.n0 = 0;
   g.dt = d->dt;
@@ -340,6 +347,9 @@ static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace&
   p.src = static_cast<const float*>(in[B200FDTD_IN_SOURCE_FIELD]);
   p.wave = static_cast<const float*>(in[B200FDTD_IN_SOURCE_WAVEFORM]);
   p.out = static_cast<float*>(out[0]);
+  p.proj = d->proj_rows > 0 ? static_cast<const float*>(in[B200FDTD_IN_PROJECTION]) : nullptr;
+  if (d->proj_rows > 0)   // the accumulators start from zero
+    CUDA_TRY(cudaMemsetAsync(p.out, 0, (size_t)d->proj_rows * 3 * d->xx * d->yy * d->zz * sizeof(float), st));
 
   CUDA_TRY(cudaMemsetAsync(ws, 0, w.zero_end, st));
   float* S = reinterpret_cast<float*>(ws + w.S);
@@ -401,6 +411,8 @@ static int run_impl(const b200fdtd_desc* d, const void* const* in, void* const* 
   for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i)
     if (!in[i]) return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i);
   if (num_outputs(d) > 0 && !out[0]) return fail(B200FDTD_EINVAL, "outputs[0] is NULL");
+  if (d->proj_rows > 0 && !in[B200FDTD_IN_PROJECTION])
+    return fail(B200FDTD_EINVAL, "inputs[%d] (projection weights) is NULL", B200FDTD_IN_PROJECTION);
   const Geom g = make_geom(d);
   if ((long long)g.Y * g.Zq > INT_MAX / 8) return fail(B200FDTD_EUNSUPPORTED, "plane too large");
   if (g.X > 65535 && d->kernel == B200FDTD_KERNEL_TWOPASS)
@@ -450,7 +462,8 @@ int b200fdtd_num_outputs(const b200fdtd_desc* desc) {
 
 size_t b200fdtd_output_bytes(const b200fdtd_desc* desc) {
   if (validate(desc)) return 0;
-  return (size_t)num_outputs(desc) * 3 * desc->xx * desc->yy * desc->zz * sizeof(float);
+  const size_t n = desc->proj_rows > 0 ? (size_t)desc->proj_rows : (size_t)num_outputs(desc);
+  return n * 3 * desc->xx * desc->yy * desc->zz * sizeof(float);
 }
 
 size_t b200fdtd_workspace_bytes(const b200fdtd_desc* desc) {
@@ -474,7 +487,9 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
   if (!hin || !hout) return fail(B200FDTD_EINVAL, "inputs/outputs is NULL");
   CUDA_TRY(cudaSetDevice(device));
   const size_t XY = (size_t)d->X * d->Y;
-  size_t bytes[B200FDTD_NUM_INPUTS];
+  size_t bytes[B200FDTD_MAX_INPUTS];
+  const int nin = d->proj_rows > 0 ? B200FDTD_MAX_INPUTS : B200FDTD_NUM_INPUTS;
+  bytes[B200FDTD_IN_PROJECTION] = (size_t)d->proj_rows * (num_outputs(d) > 0 ? num_outputs(d) : 0) * 4;
   bytes[B200FDTD_IN_EPSILON] = 3 * (size_t)d->xx * d->yy * d->zz * 4;
   bytes[B200FDTD_IN_SOURCE_FIELD] =
       (d->source_axis == 0 ? 2 * (size_t)d->Y * d->Z
@@ -487,7 +502,7 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
   const size_t ws_bytes = b200fdtd_workspace_bytes(d);
   if (ws_bytes == 0) return B200FDTD_EINVAL;
   cudaStream_t st = nullptr;
-  void* din[B200FDTD_NUM_INPUTS] = {nullptr};
+  void* din[B200FDTD_MAX_INPUTS] = {nullptr};
   void* dout[1] = {nullptr};
   void* ws = nullptr;
   rc = B200FDTD_OK;
@@ -506,7 +521,7 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
     }                                                                                       \
   } while (0)
   TRY_CLEAN(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i) {
+  for (int i = 0; i < nin; ++i) {
     if (!hin[i]) { cleanup(); return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i); }
     TRY_CLEAN(cudaMalloc(&din[i], bytes[i]));
     TRY_CLEAN(cudaMemcpyAsync(din[i], hin[i], d->tt > 0 || i != B200FDTD_IN_SOURCE_WAVEFORM
@@ -535,10 +550,13 @@ void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
   }
   b200fdtd_desc d;
   memcpy(&d, opaque, sizeof d);
-  void* outs[1] = {buffers[B200FDTD_NUM_INPUTS]};
+  // operands: the 7 arrays (+ the projection matrix when proj_rows > 0), then result, scratch
+  const int nin = d.proj_rows > 0 ? B200FDTD_MAX_INPUTS : B200FDTD_NUM_INPUTS;
+  const void* ins[B200FDTD_MAX_INPUTS] = {nullptr};
+  for (int i = 0; i < nin; ++i) ins[i] = buffers[i];
+  void* outs[1] = {buffers[nin]};
   const size_t ws_bytes = b200fdtd_workspace_bytes(&d);
-  run_impl(&d, const_cast<const void* const*>(buffers), outs, buffers[B200FDTD_NUM_INPUTS + 1],
-           ws_bytes, static_cast<cudaStream_t>(stream));
+  run_impl(&d, ins, outs, buffers[nin + 1], ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
@@ -559,6 +577,41 @@ int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
     info[3] = kTwoPassThreads;
     info[4] = (int64_t)((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads) * g.X;
   }
+  return B200FDTD_OK;
+}
+
+
+// ---- adjoint product-reduce -----------------------------------------------------
+
+int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* fields,
+                            const void* coef, void* out, void* stream) {
+  if (nports < 1 || nports > kAdjMaxPorts)
+    return fail(B200FDTD_EINVAL, "nports must be in [1, %d], got %d", kAdjMaxPorts, nports);
+  if (ww < 1 || ww > 64) return fail(B200FDTD_EINVAL, "ww must be in [1, 64], got %d", ww);
+  if (!fields || !coef || !out) return fail(B200FDTD_EINVAL, "fields/coef/out is NULL");
+  AdjFields f;
+  for (int i = 0; i < kAdjMaxPorts; ++i) f.f[i] = nullptr;
+  for (int i = 0; i < nports; ++i) {
+    if (!fields[i]) return fail(B200FDTD_EINVAL, "fields[%d] is NULL", i);
+    f.f[i] = static_cast<const float2*>(fields[i]);
+  }
+  if (nvox == 0) return B200FDTD_OK;
+  int sms = 0, l2 = 0;
+  int rc = device_props(&sms, &l2);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float2* c = static_cast<const float2*>(coef);
+  float* o = static_cast<float*>(out);
+  cudaError_t e = cudaSuccess;
+  switch (nports) {
+#define ADJ_CASE(N) case N: e = adjoint_reduce_launch<N>(f, c, ww, nvox, o, sms, st); break;
+    ADJ_CASE(1) ADJ_CASE(2) ADJ_CASE(3) ADJ_CASE(4) ADJ_CASE(5) ADJ_CASE(6) ADJ_CASE(7) ADJ_CASE(8)
+    ADJ_CASE(9) ADJ_CASE(10) ADJ_CASE(11) ADJ_CASE(12) ADJ_CASE(13) ADJ_CASE(14) ADJ_CASE(15)
+    ADJ_CASE(16)
+#undef ADJ_CASE
+  }
+  if (e != cudaSuccess)
+    return fail(B200FDTD_ECUDA, "adjoint_reduce launch failed: %s", cudaGetErrorString(e));
   return B200FDTD_OK;
 }
 

@@ -22,6 +22,7 @@ struct Geom {
   int ox, oy, oz;      // ... and its offset
   int src_axis, src_pos;
   int out_start, out_stop, out_step;
+  int proj_rows, n_out; // fused projection: rows of W (0 = plain snapshots), snapshots per run
   int tt;              // one past the last step of this launch
   int n0;              // first step of this launch (stepping sessions; 0 for a whole run)
   float dt;
@@ -48,7 +49,8 @@ struct Ptrs {
   float* psiE[2];
   const float* src;    // source_field, caller layout
   const float* wave;   // (tt,2)
-  float* out;          // (n_out,3,xx,yy,zz)
+  float* out;          // (n_out,3,xx,yy,zz), or (proj_rows,3,xx,yy,zz) with the fused projection
+  const float* proj;   // (proj_rows, n_out) projection weights, or nullptr
 };
 
 template <typename T> struct VecTraits;
@@ -226,14 +228,35 @@ __device__ __forceinline__ void add_source(const Geom& g, const float* __restric
   }
 }
 
-// Snapshot of the VW cells (x, y, q*VW..) into out[oi] (n_out,3,xx,yy,zz), cropped.
+// Snapshot of the VW cells (x, y, q*VW..) into out[oi] (n_out,3,xx,yy,zz), cropped.  With the
+// fused projection (g.proj_rows = R > 0) the snapshot is not stored: every row r of the output
+// (R,3,xx,yy,zz) accumulates W[r][oi] * E instead (one fmaf per row, snapshot order -- the order
+// oracle/fdtd_c.c:oracle_fdtd_project restates).  Successive snapshot steps of one cell are
+// ordered by the kernels' own step-to-step dependencies; the accumulators bypass L1.
 template <int VW>
 __device__ __forceinline__ void write_snapshot(const Geom& g, float* __restrict__ out, int oi,
                                                int x, int y, int q, const float (&ex)[VW],
-                                               const float (&ey)[VW], const float (&ez)[VW]) {
+                                               const float (&ey)[VW], const float (&ez)[VW],
+                                               const float* __restrict__ proj = nullptr) {
   const int sx = x - g.ox, sy = y - g.oy;
   if (sx < 0 || sx >= g.xx || sy < 0 || sy >= g.yy) return;
   const size_t comp = (size_t)g.xx * g.yy * g.zz;
+  if (g.proj_rows > 0) {
+    float* o = out + ((size_t)sx * g.yy + sy) * g.zz;
+    for (int r = 0; r < g.proj_rows; ++r, o += 3 * comp) {
+      const float w = __ldg(proj + (size_t)r * g.n_out + oi);
+#pragma unroll
+      for (int i = 0; i < VW; ++i) {
+        const int sz = q * VW + i - g.oz;
+        if (sz >= 0 && sz < g.zz) {
+          __stcg(o + sz, fmaf(w, ex[i], __ldcg(o + sz)));
+          __stcg(o + comp + sz, fmaf(w, ey[i], __ldcg(o + comp + sz)));
+          __stcg(o + 2 * comp + sz, fmaf(w, ez[i], __ldcg(o + 2 * comp + sz)));
+        }
+      }
+    }
+    return;
+  }
   float* o = out + (size_t)oi * 3 * comp + ((size_t)sx * g.yy + sy) * g.zz;
 #pragma unroll
   for (int i = 0; i < VW; ++i) {

@@ -526,7 +526,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvA), arr_to_f4(psxA)); __stcg(wPy + (pP + pvA), arr_to_f4(psyA));
             __stcg(ePx + (pP + pvA), arr_to_f4(qsx)); __stcg(ePy + (pP + pvA), arr_to_f4(qsy));
           }
-          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yA, q, exA, eyA, ezA);
+          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yA, q, exA, eyA, ezA, p.proj);
         }
         if (doHB) {
           float b0[VW], b1[VW], b2[VW], qsx[VW], qsy[VW];
@@ -552,7 +552,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvB), arr_to_f4(psxB)); __stcg(wPy + (pP + pvB), arr_to_f4(psyB));
             __stcg(ePx + (pP + pvB), arr_to_f4(qsx)); __stcg(ePy + (pP + pvB), arr_to_f4(qsy));
           }
-          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yB, q, exB, eyB, ezB);
+          if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yB, q, exB, eyB, ezB, p.proj);
         }
         // every store of sweep indices <= i has been issued by this warp
         __syncwarp();

@@ -368,7 +368,7 @@ systolic_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* 
               ex[i] = round_store<T>(ex[i]); ey[i] = round_store<T>(ey[i]);
               ez[i] = round_store<T>(ez[i]);
             }
-            write_snapshot<VW>(g, p.out, oi, P, y, q, ex, ey, ez);
+            write_snapshot<VW>(g, p.out, oi, P, y, q, ex, ey, ez, p.proj);
           }
         }
       }

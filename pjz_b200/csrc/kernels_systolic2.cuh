@@ -535,7 +535,7 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
                 ex[k][v] = round_store<T>(ex[k][v]); ey[k][v] = round_store<T>(ey[k][v]);
                 ez[k][v] = round_store<T>(ez[k][v]);
               }
-              write_snapshot<VW>(g, p.out, oi, P, yk[k], q, ex[k], ey[k], ez[k]);
+              write_snapshot<VW>(g, p.out, oi, P, yk[k], q, ex[k], ey[k], ez[k], p.proj);
             }
           }
         }

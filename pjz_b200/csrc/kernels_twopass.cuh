@@ -183,7 +183,7 @@ twopass_e_kernel(Geom g, Ptrs<T> p, int n) {
     for (int i = 0; i < VW; ++i) {
       ex[i] = round_store<T>(ex[i]); ey[i] = round_store<T>(ey[i]); ez[i] = round_store<T>(ez[i]);
     }
-    write_snapshot<VW>(g, p.out, oi, x, y, q, ex, ey, ez);
+    write_snapshot<VW>(g, p.out, oi, x, y, q, ex, ey, ez, p.proj);
   }
 }
 

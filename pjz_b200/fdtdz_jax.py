@@ -43,7 +43,7 @@ class Desc(ctypes.Structure):
               [("dt", ctypes.c_float)] +
               [(n, ctypes.c_int32) for n in ("kernel", "tile_y", "stages", "threads",
                                              "prefetch", "cols")] +
-              [("reserved", ctypes.c_int32 * 2)])
+              [("proj_rows", ctypes.c_int32), ("reserved", ctypes.c_int32)])
 
 
 _lib = None
@@ -91,7 +91,7 @@ def _shape(a):
 
 def make_desc(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
               pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
-              use_reduced_precision, launch_params, offset):
+              use_reduced_precision, launch_params, offset, output_projection=None):
   """Shape-checks the arguments the way the reference wrapper would and fills the descriptor."""
   es, ss, ws, ms = (_shape(a) for a in (epsilon, source_field, source_waveform,
                                          absorption_mask))
@@ -141,10 +141,20 @@ def make_desc(epsilon, dt, source_field, source_waveform, source_position, absor
   d.kernel = _KERNELS[k]
   d.tile_y, d.stages, d.threads, d.prefetch, d.cols = (
       int(lp.get(n, 0)) for n in ("tile_y", "stages", "threads", "prefetch", "cols"))
+  if output_projection is not None:
+    ps = _shape(output_projection)
+    nout = len(range(*d_output_steps(d)))
+    if len(ps) != 2 or ps[1] != nout or ps[0] < 1:
+      raise ValueError(f"output_projection must have shape (rows, {nout}), got {ps}")
+    d.proj_rows = ps[0]
   rc = lib().b200fdtd_validate(ctypes.byref(d))
   if rc != 0:
     raise ValueError(_last_error())
   return d
+
+
+def d_output_steps(d):
+  return (d.out_start, d.out_stop, d.out_step)
 
 
 def _void_array(ptrs):
@@ -156,17 +166,24 @@ def _void_array(ptrs):
 
 def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
           pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps, use_reduced_precision,
-          launch_params=None, offset=(0, 0, 0)):
+          launch_params=None, offset=(0, 0, 0), *, output_projection=None):
   """Execute an FDTD simulation; signature of ``fdtdz_jax.fdtdz`` as called at
   /root/reference/src/pjz/_field.py:254-269.  Returns ``(n_out, 3, xx, yy, zz)`` float32 E
-  snapshots for the steps ``range(*output_steps)``."""
+  snapshots for the steps ``range(*output_steps)``.
+
+  Extension (keyword-only, default off): ``output_projection`` = a ``(rows, n_out)`` matrix W
+  fuses the frequency projection of /root/reference/src/pjz/_field.py:272-279 into the time
+  stepping: the result is ``(rows, 3, xx, yy, zz)`` with ``out[r] = sum_s W[r, s] * snapshot_s``
+  and no snapshot is written."""
   arrays = [epsilon, source_field, source_waveform, absorption_mask, pml_kappa, pml_sigma,
             pml_alpha]
+  if output_projection is not None:
+    arrays.append(output_projection)
   d = make_desc(epsilon, dt, source_field, source_waveform, source_position, absorption_mask,
                 pml_kappa, pml_sigma, pml_alpha, pml_widths, output_steps,
-                use_reduced_precision, launch_params, offset)
+                use_reduced_precision, launch_params, offset, output_projection)
   L = lib()
-  nout = L.b200fdtd_num_outputs(ctypes.byref(d))
+  nout = d.proj_rows if d.proj_rows > 0 else L.b200fdtd_num_outputs(ctypes.byref(d))
   out_shape = (nout, 3, d.xx, d.yy, d.zz)
   cuda_dev = None
   for a in arrays:
@@ -206,6 +223,41 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
       raise RuntimeError(f"b200fdtd_run failed ({rc}): {_last_error()}")
     # ws/dev are released to torch's caching allocator, which is stream-ordered.
     return out
+
+
+def adjoint_reduce(fields, coef):
+  """``out[c,x,y,z] = sum_ij sum_w Re(coef[i,j,w] * fields[i][w] * fields[j][w])`` in one pass
+  (``b200fdtd_adjoint_reduce``; replaces the N^2 volume temporaries of
+  /root/reference/src/pjz/_field.py:380-398).  ``fields``: N CUDA complex64 tensors
+  ``(ww, 3, xx, yy, zz)``; ``coef``: complex ``(N, N, ww)``.  Returns float32 ``(3, xx, yy, zz)``."""
+  import torch
+  n = len(fields)
+  f0 = fields[0]
+  if not (_is_torch(f0) and f0.is_cuda):
+    raise RuntimeError("adjoint_reduce needs CUDA tensors (no CPU fallback)")
+  dev = f0.device
+  fs = [f.to(torch.complex64).contiguous() for f in fields]
+  ww = int(f0.shape[0])
+  nvox = int(f0[0].numel())
+  for f in fs:
+    if tuple(f.shape) != tuple(f0.shape) or f.device != dev:
+      raise ValueError("all phasor fields must share shape and device")
+  c = torch.as_tensor(coef, device=dev).to(torch.complex64).contiguous()
+  if tuple(c.shape) != (n, n, ww):
+    raise ValueError(f"coef must have shape ({n}, {n}, {ww}), got {tuple(c.shape)}")
+  out = torch.empty(tuple(f0.shape[1:]), dtype=torch.float32, device=dev)
+  L = lib()
+  L.b200fdtd_adjoint_reduce.restype = ctypes.c_int
+  L.b200fdtd_adjoint_reduce.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]
+  with torch.cuda.device(dev):
+    rc = L.b200fdtd_adjoint_reduce(n, ww, nvox, _void_array([f.data_ptr() for f in fs]),
+                                   c.data_ptr(), out.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream)
+  if rc != 0:
+    raise RuntimeError(f"b200fdtd_adjoint_reduce failed ({rc}): {_last_error()}")
+  return out
 
 
 def plan_info(**kwargs):

@@ -119,7 +119,25 @@ def test_scatter_backward_is_pjz_reciprocity_formula():
   sv = scatter(e, *args, engine=fdtd_c.fdtdz)
   loss = torch.real(sv[0][1]).sum()
   loss.backward()
-  _, grads, fields = glue._scatter_impl(torch.from_numpy(eps), *args, engine=fdtd_c.fdtdz)
+  _, grads, fields, _ = glue._scatter_impl(torch.from_numpy(eps), *args, engine=fdtd_c.fdtdz)
   want = torch.sum(torch.real(grads[0][1]), dim=0)
   torch.testing.assert_close(e.grad, want, rtol=1e-5, atol=1e-7)
   assert e.grad.shape == eps.shape and float(e.grad.abs().max()) > 0
+
+
+def test_fused_projection_equals_snapshot_projection_on_the_oracle():
+  """field(fuse_projection=True) hands the pinv weights to the engine (``output_projection``)
+  and must agree with the reference flow (snapshots + pinv einsum, _field.py:272-279)."""
+  from oracle import fdtd_c
+  from pjz_b200 import SimParams, field
+  omega = np.array([2 * np.pi / 37, 2 * np.pi / 33])
+  eps = np.ones((3, 24, 18, 12), np.float32)
+  eps[:, :, 6:12, 4:8] = 12.25
+  src = np.random.default_rng(3).standard_normal((2, 1, 18, 12)).astype(np.float32)
+  p = SimParams(omega_range=(omega[0], omega[1]), tt=600, dt=0.5, absorption_padding=6,
+                absorption_coeff=4e-3, pml_widths=(4, 4), use_reduced_precision=False,
+                domain_zz=20)
+  want = field(eps, src, omega, 5, p, engine=fdtd_c.fdtdz)
+  got = field(eps, src, omega, 5, p, engine=fdtd_c.fdtdz, fuse_projection=True)
+  assert got.shape == want.shape == (2, 3, 24, 18, 12)
+  torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-6 * float(want.abs().max()))

@@ -111,3 +111,21 @@ def test_bad_shapes_raise():
     fdtd_c.fdtdz(**kw)
   with pytest.raises(ValueError):
     fdtd_numpy.fdtdz(**kw)
+
+
+def test_projection_extension_c_vs_spec():
+  """``output_projection`` (engine extension): C oracle's fmaf running sum vs the float64 spec's
+  einsum over the same snapshots; and it is exactly W @ snapshots in exact arithmetic."""
+  from oracle import fdtd_c, fdtd_numpy
+  from tests.problems import random_problem
+  kw = random_problem(domain=(10, 9, 12), axis=2, pml=(3, 3), tt=20, seed=4, output_steps=(4, 20, 5))
+  W = np.random.default_rng(1).standard_normal((3, 4)).astype(np.float32)
+  snaps = fdtd_c.fdtdz(**kw)
+  got = fdtd_c.fdtdz(**kw, output_projection=W)
+  spec = fdtd_numpy.fdtdz(**kw, output_projection=W)
+  assert got.shape == spec.shape == (3,) + snaps.shape[1:]
+  ref = np.einsum("rs,s...->r...", W.astype(np.float64), snaps.astype(np.float64))
+  np.testing.assert_allclose(got, ref, rtol=0, atol=4e-7 * np.abs(ref).max())
+  assert np.linalg.norm(got - spec) <= 1e-5 * np.linalg.norm(spec)
+  with pytest.raises(ValueError):
+    fdtd_c.fdtdz(**kw, output_projection=W[:, :3])

@@ -298,3 +298,102 @@ def test_field_through_cuda_engine_matches_oracle_engine():
   assert got.is_cuda and got.dtype == torch.complex64
   # snapshots are bit-identical; the pinv projection einsum runs on the GPU vs the CPU
   torch.testing.assert_close(got.cpu(), want, rtol=1e-5, atol=1e-6 * float(want.abs().max()))
+
+
+# ---- fused frequency projection ---------------------------------------------
+
+@pytest.mark.parametrize("kernel,domain,pml", [
+    ("twopass", (12, 10, 16), (3, 4)), ("systolic", (12, 10, 16), (3, 4)),
+    ("systolic_async", (14, 11, 24), (4, 4)), ("systolic_tma", (12, 10, 16), (3, 4)),
+    ("systolic_lean", (9, 21, 128), (16, 16)), ("auto", (7, 30, 126), (4, 6))])
+def test_fused_projection_is_bit_exact(kernel, domain, pml):
+  """``output_projection``: the kernels accumulate W[:, s] * snapshot_s in place at every output
+  step (no snapshot is written); bit-exact against the C oracle's fmaf running sum."""
+  for axis in (0, 2):
+    kw = random_problem(domain=domain, axis=axis, pml=pml, tt=33, seed=91 + axis,
+                        output_steps=(8, 33, 4))
+    W = np.random.default_rng(7).standard_normal((4, len(range(8, 33, 4)))).astype(np.float32)
+    want = fdtd_c.fdtdz(**kw, output_projection=W)
+    dev = dict(kw)
+    dev["launch_params"] = {"kernel": kernel}
+    dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+    got = fdtdz_jax.fdtdz(**dev, output_projection=W)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    host = dict(kw)
+    host["launch_params"] = {"kernel": kernel}
+    np.testing.assert_array_equal(fdtdz_jax.fdtdz(**host, output_projection=W), want)  # host path
+
+
+def test_fused_projection_rejects_bad_shapes_and_reduced_matches():
+  kw = random_problem(domain=(12, 10, 16), tt=20, seed=5, output_steps=(5, 20, 5), reduced=True)
+  W = np.ones((2, 3), np.float32)
+  got = fdtdz_jax.fdtdz(**kw, output_projection=W)
+  np.testing.assert_array_equal(got, fdtd_c.fdtdz(**kw, output_projection=W))
+  with pytest.raises(ValueError):
+    fdtdz_jax.fdtdz(**kw, output_projection=np.ones((2, 4), np.float32))
+
+
+def test_field_fused_projection_on_the_gpu():
+  from pjz_b200 import SimParams, field
+  omega = np.array([2 * np.pi / 37, 2 * np.pi / 33])
+  eps = np.ones((3, 40, 30, 20), np.float32)
+  eps[:, :, 9:21, 8:12] = 12.25
+  src = np.random.default_rng(3).standard_normal((2, 1, 30, 20)).astype(np.float32)
+  p = SimParams(omega_range=(omega[0], omega[1]), tt=700, dt=0.5, absorption_padding=10,
+                absorption_coeff=4e-4, pml_widths=(6, 6), use_reduced_precision=False,
+                domain_zz=32)
+  e = torch.from_numpy(eps).cuda()
+  want = field(e, src, omega, 6, p)
+  got = field(e, src, omega, 6, p, fuse_projection=True)
+  torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-6 * float(want.abs().max()))
+
+
+# ---- SURVEY.md 8(f2): adjoint product-reduce ----------------------------------------------------
+
+@pytest.mark.parametrize("nports,ww,shape", [(1, 1, (5, 4, 3)), (2, 3, (9, 8, 7)), (4, 2, (16, 12, 10)),
+                                             (8, 4, (20, 16, 12)), (16, 1, (6, 5, 4))])
+def test_adjoint_reduce_matches_the_reference_formula(nports, ww, shape):
+  """b200fdtd_adjoint_reduce vs the mirror of pjz's N^2-temporaries formula
+  (_field.py:380-398 -> pjz_b200/_field.py:_scatter_bwd), float32 tolerance 1e-5."""
+  from pjz_b200 import _field as glue
+  g = torch.Generator(device="cpu").manual_seed(nports * 10 + ww)
+  fields = [torch.complex(torch.randn((ww, 3) + shape, generator=g),
+                          torch.randn((ww, 3) + shape, generator=g)).cuda() for _ in range(nports)]
+  amps = [torch.complex(torch.randn(ww, generator=g), torch.randn(ww, generator=g)).cuda() + 2
+          for _ in range(nports)]
+  gm = [[torch.complex(torch.randn(ww, generator=g), torch.randn(ww, generator=g)).cuda()
+         for _ in range(nports)] for _ in range(nports)]
+  grads = [[fi * fj / a[:, None, None, None, None] for fj in fields] for a, fi in zip(amps, fields)]
+  want = glue._scatter_bwd(grads, gm)
+  got = glue._scatter_bwd_fused(fields, amps, gm)
+  assert got.shape == want.shape and got.dtype == torch.float32
+  assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) <= 1e-5
+
+
+def test_scatter_gradient_through_the_fused_backward():
+  """scatter() on CUDA tensors: forward through the CUDA engine, backward through the fused
+  product-reduce kernel; same gradient as the N^2-temporaries formula."""
+  from pjz_b200 import SimParams, mode, scatter
+  from pjz_b200 import _field as glue
+  omega = np.array([2 * np.pi / 37])
+  eps = np.ones((3, 40, 30, 20), np.float32)
+  eps[:, :, 9:21, 8:12] = 12.25
+  b0, x0, _, _ = mode(eps[:, 6:7], omega, 1)
+  b1, x1, _, _ = mode(eps[:, 33:34], omega, 1)
+  m0, m1 = x0[..., 0], x1[..., 0]
+  p = SimParams(omega_range=(omega[0], omega[0]), tt=500, dt=0.5, absorption_padding=10,
+                absorption_coeff=4e-4, pml_widths=(6, 6), use_reduced_precision=False,
+                domain_zz=32)
+  args = (omega, [m0, m1], [b0[:, 0], b1[:, 0]], [6, 33], [True, False], p)
+  e = torch.from_numpy(eps).cuda().requires_grad_(True)
+  sv = scatter(e, *args, fuse_projection=True)
+  loss = sum((s.abs() ** 2).sum() for row in sv for s in row)
+  loss.backward()
+  assert e.grad is not None and e.grad.shape == e.shape and torch.isfinite(e.grad).all()
+  # reference formula on the same fields
+  svals, grads, fields, amps = glue._scatter_impl(e.detach(), *args, want_grads=True,
+                                                  fuse_projection=True)
+  # torch hands backward() g = 2 s for L = |s|^2; _Scatter.backward conjugates it
+  want = glue._scatter_bwd(grads, [[torch.conj(2 * s) for s in row] for row in svals])
+  assert rel_l2(e.grad.cpu().numpy(), want.cpu().numpy()) <= 1e-4

@@ -1,0 +1,82 @@
+"""Measurement of the SURVEY.md 8(f1)/(f2) rows on one GPU (JSON lines on stdout).
+
+f2  b200fdtd_adjoint_reduce vs the reference formula's N^2 volume temporaries (torch), GB/s of
+    algorithmic traffic (N*ww*8 B in + 4 B out per voxel-component) against the HBM copy peak.
+f1  field() on the cfg3 demux geometry with and without the fused projection (engine +
+    projection time; the time stepping dominates, the fused path saves the snapshot round trip).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def ev_time(fn, reps=5):
+  fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps
+
+
+def main():
+  from pjz_b200 import _field as glue
+  from pjz_b200 import workloads as W
+  peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+  # ---- f2 ------------------------------------------------------------------------------------------
+  for nports, ww, shape in [(4, 4, (448, 448, 96)), (8, 2, (448, 448, 96)), (2, 1, (192, 192, 96))]:
+    g = torch.Generator(device="cuda").manual_seed(1)
+    fields = [torch.view_as_complex(torch.randn((ww, 3) + shape + (2,), generator=g, device="cuda"))
+              for _ in range(nports)]
+    amps = [torch.view_as_complex(torch.randn((ww, 2), generator=g, device="cuda")) + 2 for _ in range(nports)]
+    gm = [[torch.view_as_complex(torch.randn((ww, 2), generator=g, device="cuda")) for _ in range(nports)]
+          for _ in range(nports)]
+    nvox = 3 * shape[0] * shape[1] * shape[2]
+    ms = ev_time(lambda: glue._scatter_bwd_fused(fields, amps, gm))
+
+    def ref():
+      grads = [[fi * fj / a[:, None, None, None, None] for fj in fields] for a, fi in zip(amps, fields)]
+      return glue._scatter_bwd(grads, gm)
+    ms_ref = ev_time(ref, reps=2)
+    err = float((glue._scatter_bwd_fused(fields, amps, gm) - ref()).norm() / ref().norm())
+    bytes_alg = nvox * (nports * ww * 8 + 4)
+    print(json.dumps({"row": "f2 adjoint product-reduce", "nports": nports, "ww": ww, "volume": shape,
+                      "ms": ms, "ms_torch_reference_formula": ms_ref, "speedup": ms_ref / ms,
+                      "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": peak,
+                                   "unit": "GB/s", "frac": bytes_alg / ms / 1e6 / peak},
+                      "rel_l2_vs_reference_formula": err}))
+    del fields
+    torch.cuda.empty_cache()
+  # ---- f1 ------------------------------------------------------------------------------------------
+  eps, ports, params, omega = W.demux(reduced=False)
+  params = params._replace(tt=int(os.environ.get("F1_TT", "3000")))
+  axis, pos, _ = ports[0]
+  src = W.gaussian_port_source(eps, axis, pos)
+  e = torch.from_numpy(np.ascontiguousarray(eps)).cuda()
+  res = {}
+  for fuse in (False, True):
+    glue.field(e, src, omega, pos, params, fuse_projection=fuse)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = glue.field(e, src, omega, pos, params, fuse_projection=fuse)
+    torch.cuda.synchronize()
+    res[fuse] = (time.perf_counter() - t0, out)
+    torch.cuda.empty_cache()
+  err = float((res[True][1] - res[False][1]).abs().max() / res[False][1].abs().max())
+  print(json.dumps({"row": "f1 fused frequency projection", "workload": "cfg3 demux 512x512x128, "
+                    f"{params.tt} steps, {omega.shape[0]} frequencies ({2 * omega.shape[0] + 1} snapshots)",
+                    "field_s_snapshots_then_einsum": res[False][0], "field_s_fused": res[True][0],
+                    "max_abs_diff_over_max": err}))
+
+
+if __name__ == "__main__":
+  main()
