@@ -21,6 +21,7 @@
 #include "kernels_systolic2.cuh"
 #include "kernels_systolic3.cuh"
 #include "kernels_lean.cuh"
+#include "kernels_lean1.cuh"
 #include "kernels_twopass.cuh"
 #include "postproc.cuh"
 
@@ -169,7 +170,10 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   if (rc) return rc;
   std::string why;
   if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
-    if (!lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why))
+    const bool ok = d->cols == 1
+        ? lean1_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why)
+        : lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why);
+    if (!ok)
       return fail(B200FDTD_EUNSUPPORTED, "systolic_lean kernel unavailable: %s", why.c_str());
     plan->depth = 1;
     return B200FDTD_OK;
@@ -190,6 +194,25 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {
     const int depth = d->prefetch > 0 ? d->prefetch : 1;
     if (configure_async<T>(g, d, depth, sms, l2, &plan->sys, &why)) {
+      // Short x extent: the stages of the pipeline trail each other by ~depth+6 planes around a
+      // ring of X planes, so only X/(depth+6) of them can run at once.  Rather than leaving SMs
+      // to stages that only wait, cap the stage count and cut the domain into narrower y-tiles.
+      const int cap = g.X / (depth + 6) > 1 ? g.X / (depth + 6) : 1;
+      if (d->tile_y == 0 && d->stages == 0 && plan->sys.stages > cap && plan->sys.tile_y > 2) {
+        b200fdtd_desc d2 = *d;
+        const int want_tiles = (sms + cap - 1) / cap;
+        int tile = (g.Y + want_tiles - 1) / want_tiles;
+        if (tile < 2) tile = 2;
+        if (tile < plan->sys.tile_y) {
+          d2.tile_y = tile;
+          d2.stages = cap;
+          SystolicCfg alt;
+          std::string why2;
+          if (configure_async<T>(g, &d2, depth, sms, l2, &alt, &why2) && alt.stages <= cap &&
+              (long long)alt.stages * alt.ntiles > (long long)cap * plan->sys.ntiles)
+            plan->sys = alt;
+        }
+      }
       plan->kernel = B200FDTD_KERNEL_SYSTOLIC_ASYNC;
       plan->depth = depth;
       return B200FDTD_OK;
@@ -379,7 +402,9 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
     int rc;
     if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
     else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
-      if constexpr (sizeof(T) == 4) rc = lean_launch(g, p, plan.sys, sync, st);
+      if constexpr (sizeof(T) == 4)
+        rc = plan.sys.cols == 1 ? lean1_launch(g, p, plan.sys, sync, st)
+                                : lean_launch(g, p, plan.sys, sync, st);
       else rc = (int)cudaErrorInvalidValue;
     }
     else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_TMA)
@@ -739,7 +764,9 @@ int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stre
   g.n0 = n0;
   g.tt = n0 + nsteps;
   CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
-  const int rc = lean_launch(g, s->pf, s->plan.sys, reinterpret_cast<unsigned*>(s->ws + s->w.sync), st);
+  unsigned* const sync = reinterpret_cast<unsigned*>(s->ws + s->w.sync);
+  const int rc = s->plan.sys.cols == 1 ? lean1_launch(g, s->pf, s->plan.sys, sync, st)
+                                       : lean_launch(g, s->pf, s->plan.sys, sync, st);
   if (rc != 0)
     return fail(B200FDTD_ECUDA, "systolic launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return B200FDTD_OK;

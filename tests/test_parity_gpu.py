@@ -137,6 +137,27 @@ def test_systolic_lean_ragged_domains(domain, pml, zb):
     np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean"), fdtd_c.fdtdz(**kw))
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (7, 3), (4, 40), (14, 2)])
+def test_systolic_lean_one_column_per_warp(tile_y, stages, axis):
+  """cols=1: one y-column per warp (15 compute warps), single coefficient slot refilled at the
+  end of each iteration."""
+  kw = random_problem(domain=(11, 23, 128), axis=axis, pml=(16, 16), tt=45, seed=13,
+                      output_steps=(20, 45, 6))
+  want = fdtd_c.fdtdz(**kw)
+  out = run_gpu(kw, kernel="systolic_lean", cols=1, tile_y=tile_y, stages=stages)
+  np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("domain,pml,zb", [((9, 14, 125), (3, 5), False), ((16, 1, 128), (0, 0), False),
+                                           ((12, 26, 128), (0, 0), True), ((3, 30, 126), (16, 16), False)])
+def test_systolic_lean_one_column_ragged_domains(domain, pml, zb):
+  for axis in (0, 2):
+    kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
+                        seed=7, output_steps=(5, 14, 4), absorb_pad=2, z_as_batch=zb)
+    np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean", cols=1), fdtd_c.fdtdz(**kw))
+
+
 def test_systolic_lean_rejects_other_geometries():
   kw = random_problem(domain=(8, 8, 64), tt=4, seed=1)
   with pytest.raises((ValueError, RuntimeError)):
@@ -209,6 +230,7 @@ def test_schedule_selection_and_linearity_large():
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_async"))
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_tma"))
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean"))
+  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean", cols=1))
   assert np.isfinite(a).all() and np.abs(a).max() > 0
   kw2 = dict(kw); kw2["output_steps"] = (5, 16, 10)
   np.testing.assert_array_equal(run_gpu(kw2), a[1:4:2])
