@@ -419,3 +419,18 @@ def test_scatter_gradient_through_the_fused_backward():
   # torch hands backward() g = 2 s for L = |s|^2; _Scatter.backward conjugates it
   want = glue._scatter_bwd(grads, [[torch.conj(2 * s) for s in row] for row in svals])
   assert rel_l2(e.grad.cpu().numpy(), want.cpu().numpy()) <= 1e-4
+
+
+def test_lean_long_run_matches_independent_kernel_at_baseline_size():
+  """cfg2-sized domain, 400 steps (50 pipeline rounds): the default plan -- L2 discard of
+  consumed planes and progress-gated prefetch included -- against the cp.async kernel, which
+  shares neither the staging nor the discard logic.  Bit-for-bit on three snapshots."""
+  kw = random_problem(domain=(256, 256, 128), sub=(192, 192, 96), offset=(32, 32, 16), axis=0,
+                      pml=(16, 16), tt=400, seed=6, output_steps=(150, 400, 120), absorb_pad=32,
+                      absorb_coeff=1e-4)
+  a = run_gpu(kw, kernel="systolic_async")
+  b = run_gpu(kw)                       # AUTO -> systolic_lean
+  assert fdtdz_jax.plan_info(**{**kw, "launch_params": None})["kernel"] == "systolic_lean"
+  np.testing.assert_array_equal(a, b)
+  assert np.isfinite(a).all() and np.abs(a[-1]).max() > 0
+  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean", cols=1))
