@@ -171,6 +171,16 @@ int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* 
                             const void* coef, void* out, void* stream);
 
 
+/* ---- Waveguide-mode operator --------------------------------------------------------------------
+ * y = op(x): the shifted waveguide operator of /root/reference/src/pjz/_mode.py:22-51 applied to
+ * all ww frequencies and mm trial vectors in one launch (the body of pjz.mode's subspace
+ * iteration, :101-145; the iteration itself is driven by pjz_b200/_mode_gpu.py).
+ * eps (3,uu,vv) in "propagate-along-z" form, omega (ww), shift (ww), x and y (ww,2,uu,vv,mm):
+ * all device float32.  Asynchronous on `stream`. */
+int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, const void* omega,
+                           const void* shift, const void* x, void* y, void* stream);
+
+
 /* ---- Stepping sessions ---------------------------------------------------------------------------
  * For callers that drive the time loop themselves -- the x-slab domain decomposition of
  * pjz_b200/_decomp.py exchanges halo planes between GPUs after every half-step.  A session

@@ -641,6 +641,24 @@ int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* 
 }
 
 
+// ---- waveguide-mode operator ------------------------------------------------------
+
+int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, const void* omega,
+                           const void* shift, const void* x, void* y, void* stream) {
+  if (ww < 1 || uu < 1 || vv < 1 || mm < 1)
+    return fail(B200FDTD_EINVAL, "mode_operator: extents must be positive");
+  if (!eps || !omega || !shift || !x || !y) return fail(B200FDTD_EINVAL, "mode_operator: NULL argument");
+  const size_t n = (size_t)ww * uu * vv * mm;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mode_operator_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ww, uu, vv, mm, static_cast<const float*>(eps), static_cast<const float*>(omega),
+      static_cast<const float*>(shift), static_cast<const float*>(x), static_cast<float*>(y));
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+
 // ---- stepping sessions (host-driven time loops: domain decomposition with halo exchange) ------
 
 struct b200fdtd_session {

@@ -73,3 +73,58 @@ inline cudaError_t adjoint_reduce_launch(const AdjFields& f, const float2* coef,
 }
 
 }  // namespace b200
+
+// ---- waveguide-mode operator ---------------------------------------------------
+// y = op(x) of the shifted subspace iteration of /root/reference/src/pjz/_mode.py:22-51, batched
+// over the ww frequencies and the mm trial vectors in ONE launch:
+//   a = (omega^2 eps_yx - shift) x
+//   b = (-d-_v x0 + d-_u x1) / eps_z ;  b = (-d+_v b, d+_u b) * eps_yx
+//   c = d+_u x0 + d+_v x1            ;  c = (d-_u c, d-_v c)
+//   y = a + b + c                      (d+/d- = periodic forward/backward differences)
+// x, y: (ww, 2, uu, vv, mm) float32; eps: (3, uu, vv) in "propagate-along-z" form.
+// One thread per (w, u, v, m); the 13-point neighbourhood is re-read through L1/L2 (a port
+// cross-section is a few hundred KB at most).
+namespace b200 {
+
+__global__ void __launch_bounds__(256)
+mode_operator_kernel(int ww, int uu, int vv, int mm, const float* __restrict__ eps,
+                     const float* __restrict__ omega, const float* __restrict__ shift,
+                     const float* __restrict__ x, float* __restrict__ y) {
+  const size_t n = (size_t)ww * uu * vv * mm;
+  const size_t plane = (size_t)uu * vv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i % mm);
+    size_t r = i / mm;
+    const int v = (int)(r % vv); r /= vv;
+    const int u = (int)(r % uu);
+    const int w = (int)(r / uu);
+    const float* x0 = x + ((size_t)w * 2 + 0) * plane * mm + m;
+    const float* x1 = x + ((size_t)w * 2 + 1) * plane * mm + m;
+    auto X0 = [&](int a, int b) { return x0[((size_t)a * vv + b) * mm]; };
+    auto X1 = [&](int a, int b) { return x1[((size_t)a * vv + b) * mm]; };
+    auto E = [&](int c, int a, int b) { return eps[(size_t)c * plane + (size_t)a * vv + b]; };
+    const int up = u + 1 == uu ? 0 : u + 1, um = u == 0 ? uu - 1 : u - 1;
+    const int vp = v + 1 == vv ? 0 : v + 1, vm = v == 0 ? vv - 1 : v - 1;
+    // b(a, b) = (-(x0[a][b] - x0[a][b-1]) + (x1[a][b] - x1[a-1][b])) / eps_z[a][b]
+    auto Bq = [&](int a, int b) {
+      const int am = a == 0 ? uu - 1 : a - 1, bm = b == 0 ? vv - 1 : b - 1;
+      return (-(X0(a, b) - X0(a, bm)) + (X1(a, b) - X1(am, b))) / E(2, a, b);
+    };
+    // c(a, b) = (x0[a+1][b] - x0[a][b]) + (x1[a][b+1] - x1[a][b])
+    auto Cq = [&](int a, int b) {
+      const int ap = a + 1 == uu ? 0 : a + 1, bp = b + 1 == vv ? 0 : b + 1;
+      return (X0(ap, b) - X0(a, b)) + (X1(a, bp) - X1(a, b));
+    };
+    const float om2 = omega[w] * omega[w], sh = shift[w];
+    const float e_y = E(1, u, v), e_x = E(0, u, v);
+    const float b00 = Bq(u, v), c00 = Cq(u, v);
+    const float y0 = (om2 * e_y - sh) * X0(u, v) + (-(Bq(u, vp) - b00)) * e_y + (c00 - Cq(um, v));
+    const float y1 = (om2 * e_x - sh) * X1(u, v) + (Bq(up, v) - b00) * e_x + (c00 - Cq(u, vm));
+    const size_t o = ((size_t)u * vv + v) * mm + m;
+    y[((size_t)w * 2 + 0) * plane * mm + o] = y0;
+    y[((size_t)w * 2 + 1) * plane * mm + o] = y1;
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,92 @@
+"""GPU mode solver (pjz_b200/_mode_gpu.py) against the reference's own
+known answers (/root/reference/tests/test_modes.py) and the host harness (pjz_b200/_mode.py)."""
+
+import numpy as np
+import pytest
+import torch
+
+from pjz_b200 import _mode as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _eps(prop_axis, uu=30, vv=20):
+  eps = np.ones((3, uu, vv))
+  eps[:, 9:21, 8:12] = 12.25
+  return np.expand_dims(eps, axis="xyz".find(prop_axis) + 1)
+
+
+def test_operator_kernel_matches_the_reference_operator(built):
+  """b200fdtd_mode_operator vs the NumPy restatement of _mode.py:22-51, float32 tolerance."""
+  from pjz_b200 import _mode_gpu as G
+  rng = np.random.default_rng(0)
+  ww, uu, vv, mm = 3, 17, 11, 4
+  eps = rng.uniform(1, 12, (3, uu, vv))
+  omega = rng.uniform(0.1, 0.3, ww)
+  shift = rng.uniform(-1, 1, ww)
+  x = rng.standard_normal((ww, 2, uu, vv, mm))
+  want = np.stack([np.stack([M._apply_operator(eps, omega[w], x[w, ..., m]) - shift[w] * x[w, ..., m]
+                             for m in range(mm)], axis=-1) for w in range(ww)])
+  t = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+  got = G._apply(t(eps), t(omega), t(shift), t(x)).cpu().numpy()
+  assert np.linalg.norm(got - want) <= 2e-6 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("prop_axis", ["x", "y", "z"])
+def test_correct_betas(prop_axis, built):
+  # /root/reference/tests/test_modes.py:34-47
+  from pjz_b200._mode_gpu import mode_gpu
+  expected = (0.36388508, 0.18891069, 0.15406249, 0.13549446)
+  beta, field, err, iters = mode_gpu(_eps(prop_axis), np.array([2 * np.pi / 37]), num_modes=4)
+  assert beta.is_cuda and beta.dtype == torch.float32 and field.dtype == torch.float32
+  assert beta[0, :].cpu().numpy() == pytest.approx(expected, rel=1e-3)
+  uu, vv = 30, 20
+  assert tuple(field.shape) == {"x": (1, 2, 1, uu, vv, 4), "y": (1, 2, uu, 1, vv, 4),
+                                "z": (1, 2, uu, vv, 1, 4)}[prop_axis]
+  assert float(err.max()) <= 1e-4 and iters >= 1
+
+
+@pytest.mark.parametrize("prop_axis", ["x", "y", "z"])
+def test_warm_start_converges_in_one_iteration(prop_axis, built):
+  # /root/reference/tests/test_modes.py:50-73
+  from pjz_b200._mode_gpu import mode_gpu
+  omega = np.array([2 * np.pi / 37])
+  beta, field, _, _ = mode_gpu(_eps(prop_axis), omega, num_modes=1)
+  beta2, _, _, iters = mode_gpu(_eps(prop_axis), omega, num_modes=1, init=field)
+  np.testing.assert_array_almost_equal(beta.cpu().numpy(), beta2.cpu().numpy(), decimal=3)
+  assert iters == 1
+
+
+@pytest.mark.parametrize("prop_axis", ["x", "y", "z"])
+def test_unit_poynting_self_consistency_and_agreement_with_the_host_harness(prop_axis, built):
+  # /root/reference/tests/test_modes.py:76-115, batched over 3 frequencies
+  from pjz_b200 import mode
+  from pjz_b200._mode_gpu import mode_gpu
+  ww, mm = 3, 2
+  omega = np.linspace(2 * np.pi / 37, 2 * np.pi / 36, ww)
+  epsilon = _eps(prop_axis)
+  beta, field, _, _ = mode_gpu(epsilon, omega, num_modes=mm)
+  beta, field = beta.cpu().numpy(), field.cpu().numpy()
+  host_beta, _, _, _ = mode(epsilon, omega, num_modes=mm)
+  assert beta == pytest.approx(host_beta, rel=1e-3)
+  if prop_axis == "x":
+    f = np.flip(field[:, :, 0, :, :, :], axis=1)
+    epsilon = epsilon[(1, 2, 0), ...]
+  elif prop_axis == "y":
+    f = np.flip(np.swapaxes(field[:, :, :, 0, :, :], 2, 3), axis=2)
+    epsilon = np.flip(np.swapaxes(epsilon[(2, 0, 1), ...], 1, 3), axis=1)
+  else:
+    f = np.array([-1, 1])[None, :, None, None, None] * np.flip(field[:, :, :, :, 0, :], axis=1)
+  eps2 = np.squeeze(epsilon)
+  for w in range(ww):
+    for k in range(mm):
+      x = f[w, ..., k].astype(np.float64)
+      h, e, h2 = M._full_fields(float(beta[w, k]), omega[w], eps2, x)
+      assert np.linalg.norm(h - h2) / np.linalg.norm(h) < 1e-2       # the reference's bound
+      assert abs(np.sum(e[0] * h[1] - e[1] * h[0]) - 1) < 1e-3
+
+
+def test_rejects_non_singleton(built):
+  from pjz_b200._mode_gpu import mode_gpu
+  with pytest.raises(ValueError):
+    mode_gpu(np.ones((3, 4, 4, 4)), np.array([0.2]), 1)

@@ -56,6 +56,26 @@ def main():
                       "rel_l2_vs_reference_formula": err}))
     del fields
     torch.cuda.empty_cache()
+  # ---- f3 ------------------------------------------------------------------------------------------
+  from pjz_b200 import mode
+  from pjz_b200._mode_gpu import mode_gpu
+  for (uu, vv), ww, mm in [((30, 20), 1, 4), ((192, 96), 4, 2)]:
+    eps1 = np.ones((3, 1, uu, vv), np.float32) * 2.25
+    eps1[:, :, uu // 2 - 6:uu // 2 + 6, vv // 2 - 4:vv // 2 + 4] = 12.25
+    om = np.linspace(2 * np.pi / 40, 2 * np.pi / 36, ww) if ww > 1 else np.array([2 * np.pi / 37])
+    mode_gpu(eps1, om, mm)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bg, _, eg, it = mode_gpu(eps1, om, mm)
+    torch.cuda.synchronize()
+    tg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    bh, _, _, _ = mode(eps1, om, mm)
+    th = time.perf_counter() - t0
+    print(json.dumps({"row": "f3 mode solver", "cross_section": [uu, vv], "ww": ww, "num_modes": mm,
+                      "gpu_s": tg, "outer_iterations": it, "max_residual": float(eg.max()),
+                      "host_arpack_s": th,
+                      "max_rel_beta_diff_vs_host": float(np.max(np.abs(bg.cpu().numpy() - bh) / bh))}))
   # ---- f1 ------------------------------------------------------------------------------------------
   eps, ports, params, omega = W.demux(reduced=False)
   params = params._replace(tt=int(os.environ.get("F1_TT", "3000")))
