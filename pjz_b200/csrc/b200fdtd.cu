@@ -24,6 +24,7 @@
 #include "kernels_lean1.cuh"
 #include "kernels_twopass.cuh"
 #include "postproc.cuh"
+#include "render.cuh"
 
 namespace b200 {
 
@@ -654,6 +655,33 @@ int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, cons
   mode_operator_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       ww, uu, vv, mm, static_cast<const float*>(eps), static_cast<const float*>(omega),
       static_cast<const float*>(shift), static_cast<const float*>(x), static_cast<float*>(y));
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+
+// ---- permittivity renderer --------------------------------------------------------
+
+size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy) {
+  if (ll < 1 || xx < 1 || yy < 1) return 0;
+  return (size_t)3 * ll * xx * yy * sizeof(float4);
+}
+
+int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
+                    const void* layer_pos, const void* grid_start, const void* grid_end,
+                    int use_simple_averaging, void* workspace, void* out, void* stream) {
+  if (ll < 1 || xx < 1 || yy < 1 || zz < 1 || m < 1)
+    return fail(B200FDTD_EINVAL, "render: ll, xx, yy, zz, m must be positive");
+  if (!layers || !grid_start || !grid_end || !workspace || !out || (ll > 1 && !layer_pos))
+    return fail(B200FDTD_EINVAL, "render: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b > 148 * 32 ? 148 * 32 : b); };
+  tile_stats_kernel<<<blocks((size_t)3 * ll * xx * yy), 256, 0, st>>>(
+      ll, xx, yy, m, static_cast<const float*>(layers), static_cast<float4*>(workspace));
+  render_combine_kernel<<<blocks((size_t)3 * xx * yy * zz), 256, 0, st>>>(
+      ll, xx, yy, zz, static_cast<const float4*>(workspace), static_cast<const float*>(layer_pos),
+      static_cast<const float*>(grid_start), static_cast<const float*>(grid_end),
+      use_simple_averaging, static_cast<float*>(out));
   CUDA_TRY(cudaGetLastError());
   return B200FDTD_OK;
 }

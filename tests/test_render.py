@@ -1,0 +1,141 @@
+"""Permittivity renderer: the golden values of
+/root/reference/tests/test_layers.py, checked on the NumPy oracle (CPU) and on the CUDA renderer
+(``pjz_b200._epsilon.render``), plus CUDA-vs-oracle on random layer stacks."""
+
+import numpy as np
+import pytest
+
+from oracle import render_numpy
+
+Z = lambda zz: (np.arange(zz)[:, None] + np.array([[-0.5, 0]]), np.arange(zz)[:, None] + np.array([[0.5, 1]]))
+
+
+def _impls():
+  return [pytest.param("oracle", id="oracle"),
+          pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+def _render(impl, layers, pos, gs, ge, m, simple=False):
+  if impl == "oracle":
+    return render_numpy.render(layers, pos, gs, ge, m, simple)
+  from pjz_b200._epsilon import render
+  return render(np.asarray(layers, np.float32), np.asarray(pos, np.float32), gs, ge, m, simple).cpu().numpy()
+
+
+SIMPLE = [
+    ((5, 0, -0.5), (0, 1, 0, 0), 1.0), ((5, 0, -0.5), (0, 2, 0, 0), 1.5), ((5, 0, -0.5), (0, 3, 0, 0), 3.0),
+    ((4, 0, -0.5), (1, 1, 0, 0), 1.0), ((4, 0, -0.5), (1, 2, 0, 0), 2.0), ((4, 0, -0.5), (1, 3, 0, 0), 3.0),
+    ((0, 5, -0.5), (1, 0, 1, 0), 1.0), ((0, 5, -0.5), (1, 0, 2, 0), 1.5), ((0, 5, -0.5), (1, 0, 3, 0), 3.0),
+    ((0, 4, -0.5), (2, 0, 1, 0), 1.0), ((0, 4, -0.5), (2, 0, 2, 0), 2.0), ((0, 4, -0.5), (2, 0, 3, 0), 3.0),
+    ((0, 0, +2.5), (2, 0, 0, 1), 1.0), ((0, 0, +2.5), (2, 0, 0, 2), 1.5), ((0, 0, +2.5), (2, 0, 0, 3), 3.0),
+    ((0, 0, +2.0), (1, 0, 0, 1), 1.0), ((0, 0, +2.0), (1, 0, 0, 2), 2.0), ((0, 0, +2.0), (1, 0, 0, 3), 3.0),
+]
+
+
+@pytest.mark.parametrize("impl", _impls())
+def test_simple(impl):
+  # /root/reference/tests/test_layers.py:8-40
+  xx, yy, zz = 4, 5, 6
+  for thresh, index, expected in SIMPLE:
+    layer = np.ones((2, 2 * xx, 2 * yy))
+    layer[1, thresh[0]:, thresh[1]:] = 3
+    out = _render(impl, layer, [thresh[2]], *Z(zz), 1)
+    assert out[index] == pytest.approx(expected, rel=1e-6), (thresh, index)
+
+
+X_THRESHOLD = [
+    (1, 3, 0, 0, 1.0), (1, 3, 0, 1, 1.5), (1, 3, 0, 2, 3.0), (2, 6, 0, 0, 1.0), (2, 6, 0, 1, 1.5),
+    (2, 6, 0, 2, 3.0), (3, 9, 0, 0, 1.0), (3, 9, 0, 1, 1.5), (3, 9, 0, 2, 3.0),
+    (3, 6, 0, 1, 3.0), (3, 7, 0, 1, 9 / 4), (3, 8, 0, 1, 9 / 5), (3, 9, 0, 1, 1.5), (3, 10, 0, 1, 9 / 7),
+    (3, 11, 0, 1, 9 / 8), (3, 12, 0, 1, 1.0),
+    (1, 4, 1, 1, 1.0), (1, 4, 1, 2, 2.0), (1, 4, 1, 3, 3.0), (2, 8, 1, 1, 1.0), (2, 8, 1, 2, 2.0),
+    (2, 8, 1, 3, 3.0), (3, 12, 1, 1, 1.0), (3, 12, 1, 2, 2.0), (3, 12, 1, 3, 3.0),
+    (3, 9, 1, 2, 3.0), (3, 10, 1, 2, 8 / 3), (3, 11, 1, 2, 7 / 3), (3, 12, 1, 2, 2.0), (3, 13, 1, 2, 5 / 3),
+    (3, 14, 1, 2, 4 / 3), (3, 15, 1, 2, 1.0),
+]
+
+
+@pytest.mark.parametrize("impl", _impls())
+def test_x_threshold(impl):
+  # /root/reference/tests/test_layers.py:43-91
+  xx, yy, zz = 4, 3, 2
+  for m, thresh, component, index, expected in X_THRESHOLD:
+    layer = np.ones((1, 2 * m * xx, 2 * m * yy))
+    layer[0, thresh:, :] = 3
+    out = _render(impl, layer, [], *Z(zz), m)
+    assert out[component, index, 0, 0] == pytest.approx(expected, rel=1e-6), (m, thresh, component, index)
+
+
+Z_THRESHOLD = [(0.00, 2, 0, 3.0), (0.25, 2, 0, 2.0), (0.50, 2, 0, 1.5), (0.75, 2, 0, 1.2), (1.00, 2, 0, 1.0),
+               (-0.50, 0, 0, 3.0), (-0.25, 0, 0, 2.5), (+0.00, 0, 0, 2.0), (+0.25, 0, 0, 1.5),
+               (+0.50, 0, 0, 1.0)]
+
+
+@pytest.mark.parametrize("impl", _impls())
+def test_z_threshold(impl):
+  # /root/reference/tests/test_layers.py:94-119
+  for thresh, component, index, expected in Z_THRESHOLD:
+    layer = np.ones((2, 2, 2))
+    layer[1] = 3
+    out = _render(impl, layer, [thresh], *Z(1), 1)
+    assert out[component, 0, 0, index] == pytest.approx(expected, rel=1e-6), (thresh, component)
+
+
+A, B3 = 1 / (0.5 * (5 / 6) + 0.5 * (2 / 3)), 1 / ((1 / 3) * (11 / 12) + (2 / 3) * (4 / 5))
+CORNER = [
+    ((0, 0, -0.5), (0, 0, 1, 0), 3.0), ((1, 0, -0.5), (0, 0, 1, 0), 1.5), ((2, 0, -0.5), (0, 0, 1, 0), 1.0),
+    ((0, 2, -0.5), (0, 0, 1, 0), 2.0), ((0, 3, -0.5), (0, 0, 1, 0), 1.0), ((0, 0, +0.0), (0, 0, 1, 0), 2.0),
+    ((0, 0, +0.5), (0, 0, 1, 0), 1.0), ((1, 2, -0.5), (0, 0, 1, 0), A), ((0, 2, +0.0), (0, 0, 1, 0), 1.5),
+    ((1, 0, +0.0), (0, 0, 1, 0), A), ((1, 2, +0.0), (0, 0, 1, 0), B3),
+    ((0, 0, -0.5), (1, 1, 0, 0), 3.0), ((2, 0, -0.5), (1, 1, 0, 0), 2.0), ((3, 0, -0.5), (1, 1, 0, 0), 1.0),
+    ((0, 1, -0.5), (1, 1, 0, 0), 1.5), ((0, 2, -0.5), (1, 1, 0, 0), 1.0), ((0, 0, +0.0), (1, 1, 0, 0), 2.0),
+    ((0, 0, +0.5), (1, 1, 0, 0), 1.0), ((2, 1, -0.5), (1, 1, 0, 0), A), ((0, 1, +0.0), (1, 1, 0, 0), A),
+    ((2, 0, +0.0), (1, 1, 0, 0), 1.5), ((2, 1, +0.0), (1, 1, 0, 0), B3),
+    ((0, 0, 0.0), (2, 1, 1, 0), 3.0), ((2, 0, 0.0), (2, 1, 1, 0), 2.0), ((3, 0, 0.0), (2, 1, 1, 0), 1.0),
+    ((0, 2, 0.0), (2, 1, 1, 0), 2.0), ((0, 3, 0.0), (2, 1, 1, 0), 1.0), ((0, 0, 0.5), (2, 1, 1, 0), 1.5),
+    ((0, 0, 1.0), (2, 1, 1, 0), 1.0), ((2, 2, 0.0), (2, 1, 1, 0), 1.5), ((0, 2, 0.5), (2, 1, 1, 0), A),
+    ((2, 0, 0.5), (2, 1, 1, 0), A), ((2, 2, 0.5), (2, 1, 1, 0), B3),
+]
+
+
+@pytest.mark.parametrize("impl", _impls())
+def test_corner(impl):
+  # /root/reference/tests/test_layers.py:122-176
+  for thresh, index, expected in CORNER:
+    layer = np.ones((2, 4, 4))
+    layer[1, thresh[0]:, thresh[1]:] = 3
+    out = _render(impl, layer, [thresh[2]], *Z(2), 1)
+    assert out[index] == pytest.approx(expected, rel=1e-6), (thresh, index)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ll,xx,yy,zz,m,simple", [(1, 5, 4, 3, 1, False), (3, 9, 7, 12, 2, False),
+                                                 (4, 16, 12, 20, 4, False), (3, 6, 5, 8, 3, True)])
+def test_cuda_renderer_matches_the_oracle_on_random_stacks(ll, xx, yy, zz, m, simple, built):
+  rng = np.random.default_rng(ll * 100 + m)
+  layers = rng.uniform(1.0, 12.25, (ll, 2 * m * xx, 2 * m * yy)).astype(np.float32)
+  pos = np.sort(rng.uniform(0.5, zz - 1.5, ll - 1)).astype(np.float32)
+  gs = (np.arange(zz)[:, None] * 1.1 + np.array([[-0.5, 0]])).astype(np.float32)   # stretched grid
+  ge = (np.arange(zz)[:, None] * 1.1 + np.array([[0.6, 1.1]])).astype(np.float32)
+  want = render_numpy.render(layers, pos, gs, ge, m, simple)
+  got = _render("cuda", layers, pos, gs, ge, m, simple)
+  assert got.shape == (3, xx, yy, zz) and got.dtype == np.float32
+  np.testing.assert_allclose(got, want, rtol=2e-6)
+
+
+@pytest.mark.gpu
+def test_epsilon_feeds_the_engine_without_leaving_the_gpu(built):
+  """pjz.epsilon -> fdtdz_jax.fdtdz on device tensors: same snapshots as with a host epsilon."""
+  import torch
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._epsilon import epsilon
+  from tests.problems import random_problem
+  rng = np.random.default_rng(5)
+  layers = rng.uniform(1.0, 12.25, (3, 2 * 8, 2 * 7)).astype(np.float32)
+  eps = epsilon(layers, np.array([3.2, 7.9], np.float32), 1, 11)
+  assert eps.is_cuda and tuple(eps.shape) == (3, 8, 7, 11)
+  kw = random_problem(domain=(12, 10, 16), sub=(8, 7, 11), offset=(2, 1, 3), tt=12, seed=3)
+  kw["epsilon"] = eps
+  a = fdtdz_jax.fdtdz(**kw).cpu().numpy()
+  kw["epsilon"] = eps.cpu().numpy()
+  np.testing.assert_array_equal(a, fdtdz_jax.fdtdz(**kw))

@@ -76,6 +76,27 @@ def main():
                       "gpu_s": tg, "outer_iterations": it, "max_residual": float(eg.max()),
                       "host_arpack_s": th,
                       "max_rel_beta_diff_vs_host": float(np.max(np.abs(bg.cpu().numpy() - bh) / bh))}))
+  # ---- f4 ------------------------------------------------------------------------------------------
+  from oracle import render_numpy
+  from pjz_b200._epsilon import render
+  for ll, xx, yy, zz, m in [(3, 448, 448, 96, 2), (3, 64, 64, 32, 2)]:
+    rng = np.random.default_rng(0)
+    layers = torch.from_numpy(rng.uniform(1, 12.25, (ll, 2 * m * xx, 2 * m * yy)).astype(np.float32)).cuda()
+    pos = np.linspace(zz / 3, 2 * zz / 3, ll - 1).astype(np.float32)
+    gs = (np.arange(zz)[:, None] + np.array([[-0.5, 0]])).astype(np.float32)
+    ge = (np.arange(zz)[:, None] + np.array([[0.5, 1]])).astype(np.float32)
+    ms = ev_time(lambda: render(layers, pos, gs, ge, m))
+    row = {"row": "f4 renderer", "layers": [ll, 2 * m * xx, 2 * m * yy], "out": [3, xx, yy, zz], "ms": ms,
+           "bytes_algorithmic": 3 * layers.numel() * 4 + 3 * xx * yy * zz * 4}
+    row["roofline"] = {"bound": "hbm", "achieved": row["bytes_algorithmic"] / ms / 1e6, "peak": peak,
+                       "unit": "GB/s", "frac": row["bytes_algorithmic"] / ms / 1e6 / peak}
+    if xx <= 64:
+      t0 = time.perf_counter()
+      want = render_numpy.render(layers.cpu().numpy(), pos, gs, ge, m)
+      row["numpy_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+      got = render(layers, pos, gs, ge, m).cpu().numpy()
+      row["max_rel_diff_vs_oracle"] = float(np.max(np.abs(got - want) / np.abs(want)))
+    print(json.dumps(row))
   # ---- f1 ------------------------------------------------------------------------------------------
   eps, ports, params, omega = W.demux(reduced=False)
   params = params._replace(tt=int(os.environ.get("F1_TT", "3000")))
