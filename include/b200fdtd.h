@@ -185,9 +185,10 @@ int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, cons
  * pjz.render / pjz.epsilon (/root/reference/src/pjz/_epsilon.py:10-155) on the GPU, writing
  * epsilon straight into the engine's input layout.  layers (ll, 2m*xx, 2m*yy), layer_pos (ll-1),
  * grid_start / grid_end (zz, 2) [column 0: Ex/Ey cells, column 1: Ez cells], out (3, xx, yy, zz):
- * all device float32; workspace: b200fdtd_render_workspace_bytes(ll, xx, yy) device bytes.
+ * all device float32; workspace: b200fdtd_render_workspace_bytes(ll, xx, yy, zz) device bytes
+ * (256-byte aligned).
  * Forward only (the reference differentiates it with jax.grad).  Asynchronous on `stream`. */
-size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy);
+size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy, int zz);
 int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
                     const void* layer_pos, const void* grid_start, const void* grid_end,
                     int use_simple_averaging, void* workspace, void* out, void* stream);

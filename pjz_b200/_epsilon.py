@@ -49,7 +49,7 @@ def render(layers, layer_pos, grid_start, grid_end, m, use_simple_averaging=Fals
   L.b200fdtd_render.restype = ctypes.c_int
   L.b200fdtd_render.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p] * 4 + [ctypes.c_int] + \
       [ctypes.c_void_p] * 3
-  ws = torch.empty(L.b200fdtd_render_workspace_bytes(ll, xx, yy), dtype=torch.uint8, device=dev)
+  ws = torch.empty(L.b200fdtd_render_workspace_bytes(ll, xx, yy, zz), dtype=torch.uint8, device=dev)
   out = torch.empty((3, xx, yy, zz), dtype=torch.float32, device=dev)
   if pos.numel() == 0:
     pos = torch.zeros(1, dtype=torch.float32, device=dev)      # never read (ll == 1)

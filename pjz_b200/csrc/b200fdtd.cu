@@ -662,9 +662,13 @@ int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, cons
 
 // ---- permittivity renderer --------------------------------------------------------
 
-size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy) {
-  if (ll < 1 || xx < 1 || yy < 1) return 0;
-  return (size_t)3 * ll * xx * yy * sizeof(float4);
+static size_t render_stats_bytes(int ll, int xx, int yy) {
+  return align_up((size_t)3 * ll * xx * yy * sizeof(float4), 256);
+}
+
+size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy, int zz) {
+  if (ll < 1 || xx < 1 || yy < 1 || zz < 1) return 0;
+  return render_stats_bytes(ll, xx, yy) + ((size_t)4 * ll * zz + 2 * zz) * sizeof(double);
 }
 
 int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
@@ -676,12 +680,15 @@ int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
     return fail(B200FDTD_EINVAL, "render: NULL argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b > 148 * 32 ? 148 * 32 : b); };
+  double* tab = reinterpret_cast<double*>(static_cast<char*>(workspace) + render_stats_bytes(ll, xx, yy));
   tile_stats_kernel<<<blocks((size_t)3 * ll * xx * yy), 256, 0, st>>>(
       ll, xx, yy, m, static_cast<const float*>(layers), static_cast<float4*>(workspace));
+  layer_overlap_kernel<<<blocks((size_t)2 * ll * zz), 256, 0, st>>>(
+      ll, zz, static_cast<const float*>(layer_pos), static_cast<const float*>(grid_start),
+      static_cast<const float*>(grid_end), tab);
   render_combine_kernel<<<blocks((size_t)3 * xx * yy * zz), 256, 0, st>>>(
-      ll, xx, yy, zz, static_cast<const float4*>(workspace), static_cast<const float*>(layer_pos),
-      static_cast<const float*>(grid_start), static_cast<const float*>(grid_end),
-      use_simple_averaging, static_cast<float*>(out));
+      ll, xx, yy, zz, static_cast<const float4*>(workspace), tab, use_simple_averaging,
+      static_cast<float*>(out));
   CUDA_TRY(cudaGetLastError());
   return B200FDTD_OK;
 }

@@ -50,11 +50,31 @@ tile_stats_kernel(int ll, int xx, int yy, int m, const float* __restrict__ layer
   }
 }
 
+// Overlap of every layer with every cell along z: u = covered fraction, uz = u * (centroid offset
+// from the cell centre), and the cell's 12 / dz^2 -- a (2, ll, zz) table for the two z staggerings
+// (column 0: Ex/Ey cells, column 1: Ez cells; _epsilon.py:47-66, 80-85).
+__global__ void layer_overlap_kernel(int ll, int zz, const float* __restrict__ layer_pos,
+                                     const float* __restrict__ grid_start,
+                                     const float* __restrict__ grid_end, double* __restrict__ tab) {
+  const int n = 2 * ll * zz;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int z = i % zz, l = (i / zz) % ll, col = i / (zz * ll);
+    const double gs = grid_start[2 * z + col], ge = grid_end[2 * z + col];
+    const double lo = l == 0 ? -INFINITY : (double)layer_pos[l - 1];
+    const double hi = l == ll - 1 ? INFINITY : (double)layer_pos[l];
+    const double p0 = fmin(fmax(lo, gs), ge), p1 = fmin(fmax(hi, gs), ge);
+    const double u = (p1 - p0) / (ge - gs);
+    tab[i] = u;
+    tab[n + i] = u * (0.5 * (p0 + p1) - 0.5 * (gs + ge));
+    if (l == 0) tab[2 * n + col * zz + z] = 12.0 / ((ge - gs) * (ge - gs));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 render_combine_kernel(int ll, int xx, int yy, int zz, const float4* __restrict__ stats,
-                      const float* __restrict__ layer_pos, const float* __restrict__ grid_start,
-                      const float* __restrict__ grid_end, int simple, float* __restrict__ out) {
+                      const double* __restrict__ tab, int simple, float* __restrict__ out) {
   const size_t n = (size_t)3 * xx * yy * zz;
+  const int nt = 2 * ll * zz;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     const int z = (int)(i % zz);
@@ -63,22 +83,17 @@ render_combine_kernel(int ll, int xx, int yy, int zz, const float4* __restrict__
     const int X = (int)(r % xx);
     const int a = (int)(r / xx);
     const int col = a == 2 ? 1 : 0;                // Ez sits half a cell up in z (:22-27)
-    const double gs = grid_start[2 * z + col], ge = grid_end[2 * z + col];
     double avg = 0, aoi = 0, gx = 0, gy = 0, gz = 0;
     for (int l = 0; l < ll; ++l) {
-      const double lo = l == 0 ? -INFINITY : (double)layer_pos[l - 1];
-      const double hi = l == ll - 1 ? INFINITY : (double)layer_pos[l];
-      const double p0 = fmin(fmax(lo, gs), ge), p1 = fmin(fmax(hi, gs), ge);
-      const double u = (p1 - p0) / (ge - gs);
-      const double zc = 0.5 * (p0 + p1) - 0.5 * (gs + ge);
+      const double u = tab[(col * ll + l) * zz + z], uz = tab[nt + (col * ll + l) * zz + z];
       const float4 t = stats[(((size_t)a * ll + l) * xx + X) * yy + Y];
-      avg += t.x * u; aoi += t.y * u; gx += t.z * u; gy += t.w * u; gz += t.x * (u * zc);
+      avg += t.x * u; aoi += t.y * u; gx += t.z * u; gy += t.w * u; gz += t.x * uz;
     }
     double v;
     if (simple) {
       v = avg;
     } else {
-      gz /= (ge - gs) * (ge - gs) / 12.0;
+      gz *= tab[2 * nt + col * zz + z];
       const double g[3] = {gx, gy, gz};
       const double ss = gx * gx + gy * gy + gz * gz;
       const double pii = g[a] * g[a] / (ss == 0 ? 1.0 : ss);

@@ -90,3 +90,50 @@ def test_rejects_non_singleton(built):
   from pjz_b200._mode_gpu import mode_gpu
   with pytest.raises(ValueError):
     mode_gpu(np.ones((3, 4, 4, 4)), np.array([0.2]), 1)
+
+
+# ---- /root/reference/tests/test_integration.py: renderer + mode solver under sub-cell shifts ---------
+
+def _rect(pos, center, widths):
+  """pjz.rect as documented in /root/reference/src/pjz/_shape.py:16-17."""
+  out = 1.0
+  for p, c, w in zip(pos, center, widths):
+    out = out * np.clip((w + 1) / 2 - np.abs(p - c), 0, 1)
+  return out
+
+
+def test_beta_spread_under_subcell_shifts_xy(built):
+  # test_integration.py:8-28: a 25x10 Si block shifted by fifths of a cell in x and y
+  from pjz_b200._epsilon import render
+  from pjz_b200._mode_gpu import mode_gpu
+  xx, yy = 30, 20
+  pos = (np.arange(2 * xx)[:, None], np.arange(2 * yy))
+  betas = []
+  for x in np.arange(0, 1, 0.2):
+    for y in np.arange(0, 1, 0.2):
+      eps = 1 + 12.25 * _rect(pos, (xx + x, yy + y), (25, 10))
+      epsilon = render(eps[None, :, :].astype(np.float32), np.array([]), np.zeros((1, 2)),
+                       np.ones((1, 2)), 1)
+      beta, _, _, _ = mode_gpu(epsilon, np.array([2 * np.pi / 37]), 1)
+      betas.append(float(beta[0, 0]))
+  assert (np.max(betas) - np.min(betas)) / 2 / np.mean(betas) <= 1e-2
+
+
+def test_beta_spread_under_subcell_shifts_xz(built):
+  # test_integration.py:31-49: a slab whose z interfaces move by fifths of a cell
+  from pjz_b200._epsilon import render
+  from pjz_b200._mode_gpu import mode_gpu
+  xx, yy, zz = 30, 1, 20
+  pos = (np.arange(2 * xx)[:, None], np.arange(2 * yy))
+  betas = []
+  for x in np.arange(0, 1, 0.2):
+    for z in np.arange(0, 1, 0.2):
+      eps = np.ones((3, 2 * xx, 2 * yy))
+      eps[1, ...] = 1 + 12.25 * _rect(pos, (xx + x, yy), (25, np.inf))
+      epsilon = render(eps.astype(np.float32), np.array([7.5, 12.5]) + z,
+                       np.arange(zz)[:, None] + np.array([[-0.5, 0]]),
+                       np.arange(zz)[:, None] + np.array([[0.5, 1.0]]), 1)
+      assert tuple(epsilon.shape) == (3, xx, 1, zz)
+      beta, _, _, _ = mode_gpu(epsilon, np.array([2 * np.pi / 37]), 1)
+      betas.append(float(beta[0, 0]))
+  assert (np.max(betas) - np.min(betas)) / 2 / np.mean(betas) <= 1e-2

@@ -10,3 +10,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:lean
 ncu -i gpurun_out/prof_lean.ncu-rep --page source --csv > gpurun_out/prof_lean_source.csv 2>/dev/null
 timeout 1200 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -1 gpurun_out/bench_reference.log
+F1_TT=2500 timeout 900 python tools/bench_postproc.py > gpurun_out/postproc.jsonl 2>&1; tail -3 gpurun_out/postproc.jsonl | cut -c1-300
