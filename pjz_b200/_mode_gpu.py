@@ -43,17 +43,19 @@ def _apply(eps, omega, shift, x):
 
 
 def _power_iteration(eps, omega, x, n):
-  """Largest-magnitude eigenvalue of the unshifted operator (the reference's ``shift``,
-  :225-231): ``n`` normalised power steps; returns the Rayleigh quotient (ww,)."""
+  """Most negative eigenvalue of the unshifted operator (what the reference uses as ``shift``,
+  :225-231): ``n`` normalised power steps.  Returns a lower bound estimate per frequency: the
+  Rayleigh quotient minus twice the residual norm minus 10 % slack."""
   zeros = torch.zeros_like(omega)
   ww = x.shape[0]
-  w = None
+  w = rho = None
   for _ in range(n):
     x = x / torch.linalg.norm(x.reshape(ww, -1), dim=1)[:, None, None, None, None]
     y = _apply(eps, omega, zeros, x)
     w = torch.sum(x * y, dim=(1, 2, 3, 4))
+    rho = torch.linalg.norm((y - w[:, None, None, None, None] * x).reshape(ww, -1), dim=1)
     x = y
-  return w
+  return w - 2.0 * rho - 0.1 * w.abs()
 
 
 def _ritz(q, aq):
@@ -92,24 +94,28 @@ def _subspace_iteration(eps, omega, lam_min, x, n, tol, keep, degree=40):
   q, _ = torch.linalg.qr(x.reshape(ww, -1, p), mode="reduced")
   theta, xr, axr = _ritz(q, op(q.reshape(shape), zeros).reshape(ww, -1, p))
   err = torch.linalg.norm(axr - theta[:, None, :] * xr, dim=1)
-  lo = lam_min - 0.05 * lam_min.abs()
+  lo = lam_min.clone()
   i = 0
   while i < n:
     i += 1
     if i > 1 or float(err[:, :keep].max()) > tol:
-      cut = theta[:, -1]                                     # damp everything below the block
-      c = (0.5 * (cut + lo)).contiguous()
-      e = 0.5 * (cut - lo)
-      # scaled three-term recurrence (normalised at the top Ritz value: no overflow in fp32)
-      b5 = lambda t: t[:, None, None, None, None]
-      sig1 = e / torch.clamp(theta[:, 0] - c, min=1e-6)
-      sig = sig1
-      y0 = xr.reshape(shape)
-      y1 = op(y0, c) * b5(sig1 / e)
-      for _ in range(2, degree + 1):
-        sig2 = 1.0 / (2.0 / sig1 - sig)
-        y0, y1 = y1, op(y1, c) * b5(2.0 * sig2 / e) - y0 * b5(sig * sig2)
-        sig = sig2
+      for _attempt in range(6):
+        cut = theta[:, -1]                                   # damp everything below the block
+        c = (0.5 * (cut + lo)).contiguous()
+        e = 0.5 * (cut - lo)
+        # scaled three-term recurrence (normalised at the top Ritz value: no overflow in fp32)
+        b5 = lambda t: t[:, None, None, None, None]
+        sig1 = e / torch.clamp(theta[:, 0] - c, min=1e-6)
+        sig = sig1
+        y0 = xr.reshape(shape)
+        y1 = op(y0, c) * b5(sig1 / e)
+        for _ in range(2, degree + 1):
+          sig2 = 1.0 / (2.0 / sig1 - sig)
+          y0, y1 = y1, op(y1, c) * b5(2.0 * sig2 / e) - y0 * b5(sig * sig2)
+          sig = sig2
+        if bool(torch.isfinite(y1).all()):
+          break
+        lo = lo - 0.5 * lo.abs()                             # spectrum reaches below the bound: widen
       q, _ = torch.linalg.qr(y1.reshape(ww, -1, p), mode="reduced")
       theta, xr, axr = _ritz(q, op(q.reshape(shape), zeros).reshape(ww, -1, p))
       err = torch.linalg.norm(axr - theta[:, None, :] * xr, dim=1)
@@ -189,7 +195,7 @@ def mode_gpu(epsilon, omega, num_modes: int, init: Optional[torch.Tensor] = None
 
   with torch.cuda.device(dev):
     lam_min = _power_iteration(e2, omega, torch.randn(mode_shape[:-1] + (1,), generator=gen).to(dev),
-                               max(shift_iters, 10))
+                               max(shift_iters, 40))
     w, x, err, iters = _subspace_iteration(e2, omega, lam_min, x0.contiguous(), max_iters, tol,
                                            keep=num_modes)
     beta = torch.sqrt(torch.clamp(w, min=0))

@@ -137,3 +137,18 @@ def test_beta_spread_under_subcell_shifts_xz(built):
       beta, _, _, _ = mode_gpu(epsilon, np.array([2 * np.pi / 37]), 1)
       betas.append(float(beta[0, 0]))
   assert (np.max(betas) - np.min(betas)) / 2 / np.mean(betas) <= 1e-2
+
+
+def test_buried_waveguide_cross_section_matches_the_host_harness(built):
+  """A cfg3-style port (Si core in a 2.25 cladding, 96x48 cells, 2 frequencies, 2 modes): betas
+  equal to the ARPACK harness, residuals below tol."""
+  from pjz_b200 import mode
+  from pjz_b200._mode_gpu import mode_gpu
+  uu, vv = 96, 48
+  eps = np.full((3, 1, uu, vv), 2.25, np.float32)
+  eps[:, :, uu // 2 - 6:uu // 2 + 6, vv // 2 - 4:vv // 2 + 4] = 12.25
+  omega = np.array([2 * np.pi / 40, 2 * np.pi / 36])
+  beta, exc, err, iters = mode_gpu(eps, omega, 2)
+  host_beta, _, _, _ = mode(eps, omega, 2)
+  assert torch.isfinite(exc).all() and float(err.max()) <= 1e-4 and iters < 100
+  assert beta.cpu().numpy() == pytest.approx(host_beta, rel=1e-4)
