@@ -243,7 +243,7 @@ struct Workspace {
   size_t psi;      // psiH[2], psiE[2]  (zeroed)
   size_t sync;     // progress counters + status (zeroed)
   size_t zero_end; // end of the zero-initialised prefix
-  size_t B, A, A4, S, tab;
+  size_t B, A, A4, S4, S, tab;
   size_t total;
 };
 
@@ -260,6 +260,7 @@ static Workspace carve(const Geom& g, bool reduced, bool systolic, const Systoli
   w.B = o;       o = align_up(o + 3 * (size_t)g.N * el, 256);
   w.A = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
   w.A4 = o;      o = align_up(o + 4 * (size_t)g.X * g.Y * sizeof(float), 256);
+  w.S4 = o;      o = align_up(o + 4 * (size_t)g.X * g.Y * sizeof(float), 256);
   w.S = o;       o = align_up(o + 3 * (size_t)g.X * g.Y * sizeof(float), 256);
   w.tab = o;     o = align_up(o + 6 * (size_t)g.Zp * sizeof(float), 256);
   w.total = o;
@@ -307,6 +308,17 @@ __global__ void prep_absorber_kernel(Geom g, const float* __restrict__ mask,
     A4[4 * (i % XY) + i / XY] = a;
     if (i < XY) A4[4 * i + 3] = 0.f;
     S[i] = (float)(1 / (1 + s * h));
+  }
+}
+
+// z-plane source (2,2,X,Y,1) repacked per column so that a kernel fetches it with one 16-byte
+// load: S4[x][y] = (ch0 Ex, ch0 Ey, ch1 Ex, ch1 Ey).
+__global__ void prep_zsource_kernel(Geom g, const float* __restrict__ src, float* __restrict__ S4) {
+  const size_t XY = (size_t)g.X * g.Y;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < XY;
+       i += (size_t)gridDim.x * blockDim.x) {
+    S4[4 * i + 0] = src[i]; S4[4 * i + 1] = src[XY + i];
+    S4[4 * i + 2] = src[2 * XY + i]; S4[4 * i + 3] = src[3 * XY + i];
   }
 }
 
@@ -360,6 +372,7 @@ static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace&
   }
   p.A = reinterpret_cast<float*>(ws + w.A);
   p.A4 = reinterpret_cast<float*>(ws + w.A4);
+  p.S4 = reinterpret_cast<float*>(ws + w.S4);
   p.tab = reinterpret_cast<float*>(ws + w.tab);
   p.psiH[0] = psi; p.psiH[1] = psi + psi_n; p.psiE[0] = psi + 2 * psi_n; p.psiE[1] = psi + 3 * psi_n;
   p.psiH2[0] = psi + 4 * psi_n; p.psiH2[1] = psi + 5 * psi_n;   // carved only for the systolic kernel
@@ -385,6 +398,8 @@ static int prepare_typed(const b200fdtd_desc* d, const Geom& g, const Workspace&
   prep_absorber_kernel<<<256, 256, 0, st>>>(
       g, static_cast<const float*>(in[B200FDTD_IN_ABSORPTION_MASK]), const_cast<float*>(p.A),
       const_cast<float*>(p.A4), S);
+  if (g.src_axis == 2)
+    prep_zsource_kernel<<<256, 256, 0, st>>>(g, p.src, const_cast<float*>(p.S4));
   prep_b_kernel<T><<<148 * 8, 256, 0, st>>>(
       g, static_cast<const float*>(in[B200FDTD_IN_EPSILON]), S, B);
   CUDA_TRY(cudaGetLastError());

@@ -40,6 +40,7 @@ struct Ptrs {
   const T* B[3];       // (dt/eps)/(1+s dt/2), 0 in the z padding
   const float* A;      // [3][X][Y]  (1-s dt/2)/(1+s dt/2)
   const float* A4;     // [X][Y][4]  the same three values packed per column (+ one pad word)
+  const float* S4;     // [X][Y][4]  z-plane source packed per column: (ch0 Ex, ch0 Ey, ch1 Ex, ch1 Ey)
   const float* tab;    // [6][Zp]    a_e,b_e,ik_e,a_h,b_h,ik_h
   float* psiH[2];      // [X][Y][npg][VW]  (psiHx, psiHy), fp32 always
   float* psiH2[2];     // ping-pong copy (systolic kernel only)

@@ -89,7 +89,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const int X = g.X, Y = g.Y;
   const int psi_row = g.npg;                       // float4 per psi row of a slot
   const int eslot_f4 = kLeanERows * ZQ;
-  const int hslot_f4 = kLeanHRows * ZQ + 8 * psi_row + 2;   // + 8 psi rows + 2 absorber rows
+  const int hslot_f4 = kLeanHRows * ZQ + 8 * psi_row + 4;   // + 8 psi rows, 2 absorber rows, 2 z-source rows
   const int warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + kLeanXR * 2 * ZQ;
   const int NWt = min(NW, (Yt + 2) / 2);           // warps with work on THIS tile (balanced tiles)
 
@@ -215,6 +215,12 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const bool srcB = g.src_axis == 1 ? (yB == sp0 || yB == sp1) : g.src_axis == 2;
   const float dt = g.dt;
   const float4* const A4 = reinterpret_cast<const float4*>(p.A4);
+  const float4* const S4 = reinterpret_cast<const float4*>(p.S4);
+  // z-plane source: staged with the coefficients (one packed 16-byte row per column); only the
+  // lane holding z-group src_pos / 4 is hit, at element src_pos % 4
+  const bool zsrc = g.src_axis == 2;
+  const bool zhit = zsrc && q == g.src_pos / VW;
+  const int zidx = g.src_pos % VW;
 
   long long st_cp = 0, st_avail = 0, st_next = 0, st_rc = 0, st_hc = 0;
   const long long st_begin = STATS ? clock64() : 0;
@@ -255,6 +261,20 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     const int cstart = n % X;
     const int oi = snapshot_index(g, n);
     const float w0 = __ldg(p.wave + 2 * (size_t)n), w1 = __ldg(p.wave + 2 * (size_t)n + 1);
+    // z-plane source on one column: same operation order as add_source() (channel 0, then 1)
+    auto zsource = [&](const float4 s, float (&ex)[VW], float (&ey)[VW]) {
+      auto one = [&](float& e0, float& e1) {
+        const float t0 = fmaf(w1, s.z, fmaf(w0, s.x, e0)), t1 = fmaf(w1, s.w, fmaf(w0, s.y, e1));
+        e0 = zhit ? t0 : e0;
+        e1 = zhit ? t1 : e1;
+      };
+      switch (zidx) {                                // warp-uniform
+        case 0: one(ex[0], ey[0]); break;
+        case 1: one(ex[1], ey[1]); break;
+        case 2: one(ex[2], ey[2]); break;
+        default: one(ex[3], ey[3]); break;
+      }
+    };
     const float4* const rEx = reinterpret_cast<const float4*>(p.Es[rb][0]);
     const float4* const rEy = reinterpret_cast<const float4*>(p.Es[rb][1]);
     const float4* const rEz = reinterpret_cast<const float4*>(p.Es[rb][2]);
@@ -331,6 +351,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         if (lane < 2 && (lane == 0 ? ownA : doHB))
           cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
                      A4 + ((unsigned)PL * (unsigned)Y + (lane == 0 ? yA : yB)));
+        if (zsrc && lane >= 2 && lane < 4 && (lane == 2 ? ownA : doHB))
+          cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
+                     S4 + ((unsigned)PL * (unsigned)Y + (lane == 2 ? yA : yB)));
       }
       if (has_psi) {
         float4* const ps = sh + kLeanHRows * ZQ + slot;
@@ -427,6 +450,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
           bh_ += pcols(ps + 6 * psi_row, ePy, nH, false);
           tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row, A4 + ((unsigned)PL * (unsigned)Y + yA), 16, bar_h);
           bh_ += 16;
+          if (zsrc) {
+            tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 2, S4 + ((unsigned)PL * (unsigned)Y + yA), 16, bar_h);
+            bh_ += 16;
+          }
         } else if (doHB) {                           // warp 0: only column B is owned
           tma_load_1d(sh + 7 * ZQ, Bx + (vP + cB_), 512, bar_h);
           tma_load_1d(sh + 9 * ZQ, By + (vP + cB_), 512, bar_h);
@@ -438,6 +465,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         if (doHB) {
           tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 1, A4 + ((unsigned)PL * (unsigned)Y + yB), 16, bar_h);
           bh_ += 16;
+          if (zsrc) {
+            tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 3, S4 + ((unsigned)PL * (unsigned)Y + yB), 16, bar_h);
+            bh_ += 16;
+          }
         }
       }
       mbar_expect_tx(bar_h, bh_);
@@ -639,7 +670,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             e_cell(hxA[v], hyA[v], hzA[v], hxz, hyz, hzmA[v], hxmA[v], hypA[v], hzpA[v], ae[v], be[v],
                    ike[v], aA.x, aA.y, aA.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], exA[v], eyA[v], ezA[v]);
           }
-          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcA)
+          if (zsrc) zsource(lds16(hcur + kLeanHRows * ZQ + 8 * psi_row + 2), exA, eyA);
+          else if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcA)
             add_source<VW>(g, p.src, w0, w1, P, yA, q, exA, eyA, ezA);
           const unsigned o = vP + tvA;
           __stcg(wHx + o, arr_to_f4(hxA)); __stcg(wHy + o, arr_to_f4(hyA)); __stcg(wHz + o, arr_to_f4(hzA));
@@ -665,7 +697,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             e_cell(hxB[v], hyB[v], hzB[v], hxz, hyz, hzA[v], hxA[v], hypB[v], hzpB[v], ae[v], be[v],
                    ike[v], aB.x, aB.y, aB.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], exB[v], eyB[v], ezB[v]);
           }
-          if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcB)
+          if (zsrc) zsource(lds16(hcur + kLeanHRows * ZQ + 8 * psi_row + 3), exB, eyB);
+          else if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcB)
             add_source<VW>(g, p.src, w0, w1, P, yB, q, exB, eyB, ezB);
           const unsigned o = vP + tvB;
           __stcg(wHx + o, arr_to_f4(hxB)); __stcg(wHy + o, arr_to_f4(hyB)); __stcg(wHz + o, arr_to_f4(hzB));
@@ -723,7 +756,7 @@ inline int lean_warps(int tile_y) { return (tile_y + 2) / 2; }
 
 inline size_t lean_smem_bytes(const Geom& g, int tile_y) {
   const size_t eslot_f4 = (size_t)kLeanERows * 32;
-  const size_t hslot_f4 = (size_t)kLeanHRows * 32 + 8 * (size_t)g.npg + 2;
+  const size_t hslot_f4 = (size_t)kLeanHRows * 32 + 8 * (size_t)g.npg + 4;
   const size_t warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + (size_t)kLeanXR * 2 * 32;
   return sizeof(float4) * warp_f4 * lean_warps(tile_y);
 }
