@@ -347,16 +347,20 @@ def local_problem_y(kw, rank, world, ghost):
   return loc, nloc, crop
 
 
-def choose_ghost(kw, world, min_ghost=8):
+def choose_ghost(kw, world, min_ghost=None):
   """Ghost width for the y-slab scheme: the smallest multiple of the systolic kernel's stage
   count >= ``min_ghost`` (a launch of G steps keeps all S pipeline stages busy only if S divides
-  G).  A pure function of the global shapes (widest slab), so every rank picks the same value."""
+  G).  ``min_ghost`` defaults to 16 for slabs of >= 384 columns (halves the exchange count for
+  3 % more redundant work; measured +3 % on 512-column slabs) and 8 below.  A pure function of
+  the global shapes (widest slab), so every rank picks the same value."""
   from . import fdtdz_jax as shim
   mask = kw["absorption_mask"]
   eps = kw["epsilon"]
   sf = kw["source_field"]
   X, Y = int(mask.shape[1]), int(mask.shape[2])
   nloc = -(-Y // world)
+  if min_ghost is None:
+    min_ghost = 16 if nloc >= 384 else 8
   axis = 2 if len(sf.shape) == 5 else (0 if sf.shape[1] == 1 else 1)
   Z = int(np.asarray(kw["pml_kappa"]).shape[0])
   zero = np.float32(0)
