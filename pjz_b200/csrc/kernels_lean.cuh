@@ -792,9 +792,10 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
   int occ = 0;
-  cfg->need_zfix = 1;                            // (re-used) unroll factor of the plane loop
-  if (const char* e = getenv("B200FDTD_LEAN_UNROLL")) cfg->need_zfix = atoi(e) == 2 ? 2 : 1;
-  const void* fn = lean_fn(cfg->need_zfix, getenv("B200FDTD_LEAN_STATS") != nullptr);
+  cfg->need_zfix = 0;
+  cfg->unroll = 1;
+  if (const char* e = getenv("B200FDTD_LEAN_UNROLL")) cfg->unroll = atoi(e) == 2 ? 2 : 1;
+  const void* fn = lean_fn(cfg->unroll, getenv("B200FDTD_LEAN_STATS") != nullptr);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -821,7 +822,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
 
 inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& cfg, unsigned* sync,
                        cudaStream_t st) {
-  const void* fn = lean_fn(cfg.need_zfix, getenv("B200FDTD_LEAN_STATS") != nullptr);
+  const void* fn = lean_fn(cfg.unroll, getenv("B200FDTD_LEAN_STATS") != nullptr);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;

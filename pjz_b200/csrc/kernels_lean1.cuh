@@ -475,7 +475,8 @@ inline bool lean1_configure(const Geom& g, bool reduced, int tile_y_req, int sta
   cfg->ntiles = ntiles;
   cfg->cols = 1;
   cfg->threads = 32 * (widest + 2);
-  cfg->need_zfix = 1;
+  cfg->need_zfix = 0;
+  cfg->unroll = 1;
   cfg->smem_bytes = (int)lean1_smem_bytes(g, widest);
   cfg->max_lead = 10;
   cfg->pf_ahead = 6;

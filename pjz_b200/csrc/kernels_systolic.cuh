@@ -49,6 +49,7 @@ struct SystolicCfg {
   int cols;              // systolic_async: adjacent columns per compute thread (1 or 2)
   int spin_ns_max;       // systolic_lean: back-off ceiling of a waiting compute warp
   int discard;           // systolic_lean: drop consumed field lines from L2 (discard.global.L2)
+  int unroll;            // systolic_lean: unroll factor of the plane loop (1 | 2)
   long long l2_window_bytes;
 };
 

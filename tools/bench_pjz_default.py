@@ -1,0 +1,34 @@
+"""Throughput on pjz's DEFAULT engine geometry (use_reduced_precision=True, 128 - sum(pml) = 96
+z-cells, /root/reference/src/pjz/_field.py:36-58) for every kernel that supports it."""
+import json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pjz_b200 import fdtdz_jax
+from tests.problems import random_problem
+
+def run(kw, reps=2, **lp):
+  kw = dict(kw); kw["launch_params"] = lp or None
+  kw["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  try:
+    fdtdz_jax.fdtdz(**kw); torch.cuda.synchronize()
+  except Exception as e:
+    return None, str(e)[:80]
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps): fdtdz_jax.fdtdz(**kw)
+  b.record(); torch.cuda.synchronize()
+  return a.elapsed_time(b) / reps, fdtdz_jax.plan_info(**kw)
+
+for reduced, Z, pml in [(True, 96, (16, 16)), (False, 32, (16, 16)), (False, 48, (8, 8)), (True, 128, (16, 16))]:
+  X = Y = 256
+  tt = 2000
+  kw = random_problem(domain=(X, Y, Z), sub=(X - 64, Y - 64, max(Z - 8, 1)), offset=(32, 32, 4), axis=0,
+                      pml=pml, tt=tt, seed=1, output_steps=(tt - 1, tt, 1), reduced=reduced,
+                      absorb_pad=32, absorb_coeff=1e-4)
+  for lp in [dict(), dict(kernel="systolic_async", cols=1), dict(kernel="systolic_async", cols=2),
+             dict(kernel="systolic"), dict(kernel="twopass")]:
+    ms, info = run(kw, **lp)
+    if ms is None:
+      print(json.dumps({"reduced": reduced, "Z": Z, "lp": lp, "error": info})); continue
+    print(json.dumps({"reduced": reduced, "grid": [X, Y, Z], "lp": lp, "gcell_s": X * Y * Z * tt / ms / 1e6,
+                      "plan": {k: info[k] for k in ("kernel", "tile_y", "stages", "threads", "ctas")}}))
