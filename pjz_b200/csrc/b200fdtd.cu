@@ -548,10 +548,12 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
   void* ws = nullptr;
   rc = B200FDTD_OK;
   auto cleanup = [&]() {
-    for (auto p : din) if (p) cudaFree(p);
-    if (dout[0]) cudaFree(dout[0]);
-    if (ws) cudaFree(ws);
-    if (st) cudaStreamDestroy(st);
+    // stream-ordered frees: the blocks go back to the device's default pool, whose release
+    // threshold is raised below so that the next call does not pay for fresh allocations
+    for (auto p : din) if (p) cudaFreeAsync(p, st);
+    if (dout[0]) cudaFreeAsync(dout[0], st);
+    if (ws) cudaFreeAsync(ws, st);
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   };
 #define TRY_CLEAN(expr)                                                                     \
   do {                                                                                      \
@@ -562,15 +564,22 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
     }                                                                                       \
   } while (0)
   TRY_CLEAN(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool = nullptr;
+    unsigned long long keep = ~0ull;               // keep freed blocks cached between calls
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaGetLastError();
+  }
   for (int i = 0; i < nin; ++i) {
     if (!hin[i]) { cleanup(); return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i); }
-    TRY_CLEAN(cudaMalloc(&din[i], bytes[i]));
+    TRY_CLEAN(cudaMallocAsync(&din[i], bytes[i] ? bytes[i] : 4, st));
     TRY_CLEAN(cudaMemcpyAsync(din[i], hin[i], d->tt > 0 || i != B200FDTD_IN_SOURCE_WAVEFORM
                                                   ? bytes[i] : 0,
                               cudaMemcpyHostToDevice, st));
   }
-  TRY_CLEAN(cudaMalloc(&dout[0], out_bytes ? out_bytes : 4));
-  TRY_CLEAN(cudaMalloc(&ws, ws_bytes));
+  TRY_CLEAN(cudaMallocAsync(&dout[0], out_bytes ? out_bytes : 4, st));
+  TRY_CLEAN(cudaMallocAsync(&ws, ws_bytes, st));
   rc = run_impl(d, din, dout, ws, ws_bytes, st);
   if (rc == B200FDTD_OK && out_bytes) {
     if (!hout[0]) { cleanup(); return fail(B200FDTD_EINVAL, "outputs[0] is NULL"); }

@@ -195,10 +195,12 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
     # Host path (NumPy in, NumPy out).
     host = [np.ascontiguousarray(a.detach().cpu().numpy() if _is_torch(a) else np.asarray(a),
                                  dtype=np.float32) for a in arrays]
-    out = np.empty(out_shape, np.float32)
-    import torch  # only to pick the device the caller selected
+    import torch  # device selection + page-locked result buffer
     if not torch.cuda.is_available():
       raise RuntimeError("fdtdz needs a CUDA device (no CPU fallback)")
+    # the snapshots come back with one device-to-host copy: land it in page-locked memory
+    # (a pageable destination is staged through a bounce buffer at a fraction of the bandwidth)
+    out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True).numpy()
     rc = L.b200fdtd_run_host(ctypes.byref(d), _void_array([h.ctypes.data for h in host]),
                              _void_array([out.ctypes.data]), torch.cuda.current_device())
     if rc != 0:
