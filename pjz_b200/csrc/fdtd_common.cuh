@@ -244,6 +244,22 @@ __device__ __forceinline__ void write_snapshot(const Geom& g, float* __restrict_
   const size_t comp = (size_t)g.xx * g.yy * g.zz;
   if (g.proj_rows > 0) {
     float* o = out + ((size_t)sx * g.yy + sy) * g.zz;
+    const int sz0 = q * VW - g.oz;
+    if (VW == 4 && (g.oz & 3) == 0 && (g.zz & 3) == 0 && sz0 >= 0 && sz0 + VW <= g.zz) {
+      // whole 16-byte vectors (aligned crop): one read-modify-write per component and row
+      for (int r = 0; r < g.proj_rows; ++r, o += 3 * comp) {
+        const float w = __ldg(proj + (size_t)r * g.n_out + oi);
+        float4* const ox = reinterpret_cast<float4*>(o + sz0);
+        float4* const oy = reinterpret_cast<float4*>(o + comp + sz0);
+        float4* const oz_ = reinterpret_cast<float4*>(o + 2 * comp + sz0);
+        float4 a = __ldcg(ox), b = __ldcg(oy), c = __ldcg(oz_);
+        a.x = fmaf(w, ex[0], a.x); a.y = fmaf(w, ex[1], a.y); a.z = fmaf(w, ex[2], a.z); a.w = fmaf(w, ex[3], a.w);
+        b.x = fmaf(w, ey[0], b.x); b.y = fmaf(w, ey[1], b.y); b.z = fmaf(w, ey[2], b.z); b.w = fmaf(w, ey[3], b.w);
+        c.x = fmaf(w, ez[0], c.x); c.y = fmaf(w, ez[1], c.y); c.z = fmaf(w, ez[2], c.z); c.w = fmaf(w, ez[3], c.w);
+        __stcg(ox, a); __stcg(oy, b); __stcg(oz_, c);
+      }
+      return;
+    }
     for (int r = 0; r < g.proj_rows; ++r, o += 3 * comp) {
       const float w = __ldg(proj + (size_t)r * g.n_out + oi);
 #pragma unroll

@@ -347,6 +347,22 @@ def test_fused_projection_is_bit_exact(kernel, domain, pml):
     np.testing.assert_array_equal(fdtdz_jax.fdtdz(**host, output_projection=W), want)  # host path
 
 
+@pytest.mark.parametrize("kernel,domain", [("systolic_lean", (9, 21, 128)), ("twopass", (10, 9, 32)),
+                                           ("systolic_async", (10, 12, 24))])
+def test_fused_projection_aligned_crop_takes_the_vector_path(kernel, domain):
+  """Crop aligned to 16 bytes in z (offset and height multiples of 4): the accumulators are
+  updated with whole float4 read-modify-writes; same bits as the oracle's running sum."""
+  X, Y, Z = domain
+  kw = random_problem(domain=domain, sub=(X - 2, Y - 3, Z - 8), offset=(1, 2, 4), axis=0, pml=(4, 4),
+                      tt=26, seed=17, output_steps=(5, 26, 5))
+  W = np.random.default_rng(3).standard_normal((3, len(range(5, 26, 5)))).astype(np.float32)
+  want = fdtd_c.fdtdz(**kw, output_projection=W)
+  dev = dict(kw)
+  dev["launch_params"] = {"kernel": kernel}
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  np.testing.assert_array_equal(fdtdz_jax.fdtdz(**dev, output_projection=W).cpu().numpy(), want)
+
+
 def test_fused_projection_rejects_bad_shapes_and_reduced_matches():
   kw = random_problem(domain=(12, 10, 16), tt=20, seed=5, output_steps=(5, 20, 5), reduced=True)
   W = np.ones((2, 3), np.float32)
