@@ -317,7 +317,11 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
 
     // Async copies of iteration `it` (plane PL): E[PL+1] -> E slot se; H, B, psi, absorber row
     // of PL -> H/B slot sh.  `ecoef` = the iteration performs an E half-step (it >= 1).
-    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first, bool ecoef) {
+    // Straight-line on purpose: columns that a warp does not own (the halo column of warp 0, the
+    // E-only column of the last warp) and the prologue plane are copied all the same -- the
+    // addresses are valid, the values unused -- because predicating two thirds of these copies
+    // on warp-uniform flags cost more instructions than the copies themselves.
+    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first, bool /*ecoef*/) {
       const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
       float4* const d = se + q;
       float4* const h = sh + q;
@@ -326,54 +330,38 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       cp_async16(d + 6 * ZQ, rEy + (vN + tvA));
       cp_async16(d + 1 * ZQ, rEx + (vN + tvB));
       cp_async16(d + 4 * ZQ, rEz + (vN + tvB));
+      cp_async16(d + 7 * ZQ, rEy + (vN + tvB));
+      cp_async16(d + 2 * ZQ, rEx + (vN + tvC));
+      cp_async16(d + 5 * ZQ, rEz + (vN + tvC));
       cp_async16(h + 0 * ZQ, rHx + (vP + tvA));
       cp_async16(h + 2 * ZQ, rHy + (vP + tvA));
       cp_async16(h + 4 * ZQ, rHz + (vP + tvA));
-      if (doHB) {
-        cp_async16(d + 7 * ZQ, rEy + (vN + tvB));
-        cp_async16(d + 2 * ZQ, rEx + (vN + tvC));
-        cp_async16(d + 5 * ZQ, rEz + (vN + tvC));
-        cp_async16(h + 1 * ZQ, rHx + (vP + tvB));
-        cp_async16(h + 3 * ZQ, rHy + (vP + tvB));
-        cp_async16(h + 5 * ZQ, rHz + (vP + tvB));
-      }
-      if (ecoef) {
-        if (ownA) {
-          cp_async16(h + 6 * ZQ, Bx + (vP + tvA));
-          cp_async16(h + 8 * ZQ, By + (vP + tvA));
-          cp_async16(h + 10 * ZQ, Bz + (vP + tvA));
-        }
-        if (doHB) {
-          cp_async16(h + 7 * ZQ, Bx + (vP + tvB));
-          cp_async16(h + 9 * ZQ, By + (vP + tvB));
-          cp_async16(h + 11 * ZQ, Bz + (vP + tvB));
-        }
-        if (lane < 2 && (lane == 0 ? ownA : doHB))
-          cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
-                     A4 + ((unsigned)PL * (unsigned)Y + (lane == 0 ? yA : yB)));
-        if (zsrc && lane >= 2 && lane < 4 && (lane == 2 ? ownA : doHB))
-          cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
-                     S4 + ((unsigned)PL * (unsigned)Y + (lane == 2 ? yA : yB)));
-      }
+      cp_async16(h + 1 * ZQ, rHx + (vP + tvB));
+      cp_async16(h + 3 * ZQ, rHy + (vP + tvB));
+      cp_async16(h + 5 * ZQ, rHz + (vP + tvB));
+      cp_async16(h + 6 * ZQ, Bx + (vP + tvA));
+      cp_async16(h + 8 * ZQ, By + (vP + tvA));
+      cp_async16(h + 10 * ZQ, Bz + (vP + tvA));
+      cp_async16(h + 7 * ZQ, Bx + (vP + tvB));
+      cp_async16(h + 9 * ZQ, By + (vP + tvB));
+      cp_async16(h + 11 * ZQ, Bz + (vP + tvB));
+      if (lane < 2)
+        cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
+                   A4 + ((unsigned)PL * (unsigned)Y + (lane == 0 ? yA : yB)));
+      if (zsrc && lane >= 2 && lane < 4)
+        cp_async16(sh + kLeanHRows * ZQ + 8 * psi_row + lane,
+                   S4 + ((unsigned)PL * (unsigned)Y + (lane == 2 ? yA : yB)));
       if (has_psi) {
         float4* const ps = sh + kLeanHRows * ZQ + slot;
         const unsigned pp = (unsigned)PL * PPn;
         cp_async16(ps, rPx + (pp + pvA));
         cp_async16(ps + 2 * psi_row, rPy + (pp + pvA));
-        if (doHB) {
-          cp_async16(ps + psi_row, rPx + (pp + pvB));
-          cp_async16(ps + 3 * psi_row, rPy + (pp + pvB));
-        }
-        if (ecoef) {
-          if (ownA) {
-            cp_async16(ps + 4 * psi_row, ePx + (pp + pvA));
-            cp_async16(ps + 6 * psi_row, ePy + (pp + pvA));
-          }
-          if (doHB) {
-            cp_async16(ps + 5 * psi_row, ePx + (pp + pvB));
-            cp_async16(ps + 7 * psi_row, ePy + (pp + pvB));
-          }
-        }
+        cp_async16(ps + psi_row, rPx + (pp + pvB));
+        cp_async16(ps + 3 * psi_row, rPy + (pp + pvB));
+        cp_async16(ps + 4 * psi_row, ePx + (pp + pvA));
+        cp_async16(ps + 6 * psi_row, ePy + (pp + pvA));
+        cp_async16(ps + 5 * psi_row, ePx + (pp + pvB));
+        cp_async16(ps + 7 * psi_row, ePy + (pp + pvB));
       }
       if (se_first) {                                // very first plane of the sweep: E[PL] too
         float4* const f = se_first + q;
@@ -382,11 +370,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         cp_async16(f + 6 * ZQ, rEy + (vP + tvA));
         cp_async16(f + 1 * ZQ, rEx + (vP + tvB));
         cp_async16(f + 4 * ZQ, rEz + (vP + tvB));
-        if (doHB) {
-          cp_async16(f + 7 * ZQ, rEy + (vP + tvB));
-          cp_async16(f + 2 * ZQ, rEx + (vP + tvC));
-          cp_async16(f + 5 * ZQ, rEz + (vP + tvC));
-        }
+        cp_async16(f + 7 * ZQ, rEy + (vP + tvB));
+        cp_async16(f + 2 * ZQ, rEx + (vP + tvC));
+        cp_async16(f + 5 * ZQ, rEz + (vP + tvC));
       }
     };
 
