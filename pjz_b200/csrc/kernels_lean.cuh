@@ -22,7 +22,11 @@
 //    index and the service warp publishes the minimum with st.release.gpu.
 //
 // All loop predicates are warp-uniform, array strides are powers of two, addresses are 32-bit
-// vector indices: about 60 instructions per cell-update instead of ~130 in systolic_async.
+// vector indices.  Measured (ncu source page, cfg2): 744 hot-path instructions per warp and plane
+// (a thread handles 2 columns x 4 z-cells: 93 per cell) with 7 compute warps / 240 registers,
+// 1044 with 8 compute warps / 160 registers (the compiler re-materialises uniform values under
+// the 168-register cap of 9 warps), ~1000 in systolic_async for the same 8 cells per thread.
+// No spills in either build.
 #pragma once
 
 #include <stdio.h>
