@@ -6,6 +6,13 @@ the `min(k+3, X)` rule and the `max_lead` throttle -- but picks the next actor t
 RANDOM among those whose counters allow it.  If the dependency rule were too weak, some
 interleaving would read a plane that is not yet written / already overwritten and the result
 would differ from the oracle.  Arithmetic is float64 NumPy in the oracle's operation order.
+
+``discard=True`` additionally models kernels_lean.cuh's ``discard.global.L2``: an actor keeps the
+E plane it loaded as "next" for the following iteration (the shared-memory ring) and, right after
+loading E^n[P+1] and H^{n-1/2}[P] in any iteration but the sweep's first, POISONS (NaN) the global
+copy of those planes on the tile's exclusive columns (tile-local 2 .. Yt-1).  A line that was not
+really dead -- read again by this tile, by a neighbour's halo, or by a later stage before being
+rewritten -- would put NaNs into the result.
 """
 
 import numpy as np
@@ -15,8 +22,10 @@ from oracle import fdtd_numpy as spec
 
 class Emulator:
 
-  def __init__(self, kw, ntiles, stages, max_lead=6, need_rule=3, seed=0):
+  def __init__(self, kw, ntiles, stages, max_lead=6, need_rule=3, seed=0, discard=False,
+               discard_first=False):
     self.kw = kw
+    self.discard, self.discard_first = discard, discard_first
     eps = np.asarray(kw["epsilon"], np.float32)
     self.st = spec.State(eps, kw["dt"], kw["absorption_mask"], kw["pml_kappa"], kw["pml_sigma"],
                          kw["pml_alpha"], kw["pml_widths"], kw["offset"], np.float64)
@@ -42,30 +51,47 @@ class Emulator:
     self.actor = {}
     for j in range(self.S):
       for t in range(self.NT):
-        self.actor[(j, t)] = dict(n=j, k=-1, hprev=None)
+        self.actor[(j, t)] = dict(n=j, k=-1, hprev=None, ecache=None)
 
   def tile(self, t):
     return t * self.Y // self.NT, (t + 1) * self.Y // self.NT
 
-  def _h_new(self, rb, P, cols):
-    """H^{n+1/2}[P] on the given columns from read set rb (returns (3,len,Z), psiH new)."""
+  def _h_new(self, rb, P, cols, a=None, k=0):
+    """H^{n+1/2}[P] on the given columns from read set rb (returns (3,len,Z), psiH new).
+
+    With ``discard`` the E plane P comes from the actor's cache (it was loaded as P+1 one
+    iteration earlier), E[P+1] and H[P] are loaded now and their exclusive columns poisoned."""
     X, Y = self.X, self.Y
     t = self.st.t
     E, H = self.E[rb], self.H[rb]
     Pn = (P + 1) % X
     cy = np.asarray(cols) % Y
-    cyp = (cy + 1) % Y
-    ex, ey, ez = E[0][P][cy], E[1][P][cy], E[2][P][cy]
+    load = np.asarray(list(cols) + [cols[-1] + 1]) % Y        # columns y0-1 .. y1 (Yt + 2 of them)
+    if self.discard and a is not None:
+      ecur = a["ecache"] if k >= 0 else np.stack([E[c][P][load] for c in range(3)])
+      enext = np.stack([E[c][Pn][load] for c in range(3)])
+      hold = np.stack([H[c][P][cy] for c in range(3)])
+      a["ecache"] = enext.copy()
+      if k >= 0 or self.discard_first:                        # never the sweep's first loads
+        dead = np.asarray(cols[2:-1]) % Y if len(cols) > 3 else np.asarray([], np.int64)
+        for c in range(3):                                    # tile-local columns 2 .. Yt-1
+          E[c][Pn][dead] = np.nan
+          H[c][P][dead] = np.nan
+    else:
+      ecur = np.stack([E[c][P][load] for c in range(3)])
+      enext = np.stack([E[c][Pn][load] for c in range(3)])
+      hold = np.stack([H[c][P][cy] for c in range(3)])
+    ex, ey, ez = ecur[0][:-1], ecur[1][:-1], ecur[2][:-1]
     dzEy = spec._dz_fwd(ey)
     dzEx = spec._dz_fwd(ex)
     px = t["b_h"] * self.psiH[rb][0][P][cy] + t["a_h"] * dzEy
     py = t["b_h"] * self.psiH[rb][1][P][cy] + t["a_h"] * dzEx
-    cx = (E[2][P][cyp] - ez) - (dzEy * t["ik_h"] + px)
-    cyv = (dzEx * t["ik_h"] + py) - (E[2][Pn][cy] - ez)
-    cz = (E[1][Pn][cy] - ey) - (E[0][P][cyp] - ex)
+    cx = (ecur[2][1:] - ez) - (dzEy * t["ik_h"] + px)
+    cyv = (dzEx * t["ik_h"] + py) - (enext[2][:-1] - ez)
+    cz = (enext[1][:-1] - ey) - (ecur[0][1:] - ex)
     dt = self.st.dt_t
-    h = np.stack([H[0][P][cy] - dt * cx, H[1][P][cy] - dt * cyv, H[2][P][cy] - dt * cz])
-    return h, np.stack([px, py])
+    h = np.stack([hold[0] - dt * cx, hold[1] - dt * cyv, hold[2] - dt * cz])
+    return h, np.stack([px, py]), (ex, ey, ez)
 
   def ready(self, j, t):
     a = self.actor[(j, t)]
@@ -95,7 +121,7 @@ class Emulator:
     y0, y1 = self.tile(t)
     P = (n % X + k) % X
     cols_h = list(range(y0 - 1, y1))            # H formed on y0-1 .. y1-1
-    h, psi = self._h_new(rb, P, cols_h)
+    h, psi, ecur = self._h_new(rb, P, cols_h, a, k)
     if k >= 0:
       own = np.arange(y0, y1)
       hx, hy, hz = h[0][1:], h[1][1:], h[2][1:]  # own columns
@@ -109,8 +135,7 @@ class Emulator:
       cy = (dzHx * tb["ik_e"] + qy) - (hz - hz_xm)
       cz = (hy - hy_xm) - (hx - hx_ym)
       A, B = self.st.A, self.st.B
-      Er = self.E[rb]
-      e = [A[c][P][own] * Er[c][P][own] + B[c][P][own] * cc for c, cc in enumerate((cx, cy, cz))]
+      e = [A[c][P][own] * ecur[c][1:] + B[c][P][own] * cc for c, cc in enumerate((cx, cy, cz))]
       # source
       w = self.wf[n]
       p = int(self.kw["source_position"])
@@ -149,7 +174,7 @@ class Emulator:
     a["hprev"] = (h[1][1:].copy(), h[2][1:].copy())
     a["k"] = k + 1
     if a["k"] == X:
-      a["n"], a["k"], a["hprev"] = n + self.S, -1, None
+      a["n"], a["k"], a["hprev"], a["ecache"] = n + self.S, -1, None, None
 
   def run(self):
     keys = list(self.actor.keys())
