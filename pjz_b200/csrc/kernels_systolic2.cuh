@@ -187,6 +187,14 @@ systolic2_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned*
           const unsigned sweep = pf_done / sweep_iters, it = pf_done % sweep_iters;
           const int n = j + (int)sweep * S;
           if (n >= g.tt) break;
+          // only planes the previous step has already produced (prefetching a plane that is
+          // about to be overwritten fetches dead data from HBM; measured in kernels_lean.cuh)
+          if (n > 0) {
+            const unsigned m = (unsigned)(n / S);
+            const unsigned need = (j > 0 ? m : m - 1u) * (unsigned)g.X +
+                                  (unsigned)min((int)it + 2, g.X);
+            if (min(v0, min(v1, v2)) < need) break;
+          }
           const int rb = n & 1;
           const int P = wrapi(n % g.X - 1 + (int)it, g.X), Pn = wrapi(P + 1, g.X);
           const int a = lane - 8;
