@@ -22,6 +22,7 @@
 #include "kernels_systolic3.cuh"
 #include "kernels_lean.cuh"
 #include "kernels_lean1.cuh"
+#include "kernels_lean16.cuh"
 #include "kernels_twopass.cuh"
 #include "postproc.cuh"
 #include "render.cuh"
@@ -171,9 +172,14 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   if (rc) return rc;
   std::string why;
   if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
-    const bool ok = d->cols == 1
+    bool ok = d->cols == 1
         ? lean1_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why)
         : lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why);
+    if (!ok && d->cols != 1 && g.Zq <= kL16ZR) {   // short columns / fp16 storage: half-warp variant
+      std::string why16;
+      ok = lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why16);
+      if (!ok) why += "; half-warp variant: " + why16;
+    }
     if (!ok)
       return fail(B200FDTD_EUNSUPPORTED, "systolic_lean kernel unavailable: %s", why.c_str());
     plan->depth = 1;
@@ -188,6 +194,15 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   }
   if (d->kernel == B200FDTD_KERNEL_AUTO &&
       lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
+    plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
+    plan->depth = 1;
+    return B200FDTD_OK;
+  }
+  // fp16 storage with 13..16 vectors per column (97 <= Z <= 128): the half-warp lean kernel
+  // (measured 107 vs 85 Gcell/s on 256x256x128; with 12 vectors a quarter of its lanes idle and
+  // it only ties with the cp.async kernel: 80 vs 82).
+  if (d->kernel == B200FDTD_KERNEL_AUTO && sizeof(T) == 2 && g.Zq >= 13 && g.Zq <= kL16ZR &&
+      lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
     plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
     plan->depth = 1;
     return B200FDTD_OK;
@@ -418,7 +433,8 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
     int rc;
     if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
     else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
-      if constexpr (sizeof(T) == 4)
+      if (plan.sys.cols == 16) rc = lean16_launch<T>(g, p, plan.sys, sync, st);
+      else if constexpr (sizeof(T) == 4)
         rc = plan.sys.cols == 1 ? lean1_launch(g, p, plan.sys, sync, st)
                                 : lean_launch(g, p, plan.sys, sync, st);
       else rc = (int)cudaErrorInvalidValue;
@@ -746,7 +762,7 @@ static int session_plan(const b200fdtd_desc* desc, const Geom& g, Plan* plan, bo
     if (desc->kernel == B200FDTD_KERNEL_AUTO) return B200FDTD_OK;
     return rc;
   }
-  if (p.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
+  if (p.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN && p.sys.cols != 16) {
     *plan = p;
     *systolic = true;
   } else if (desc->kernel != B200FDTD_KERNEL_AUTO) {

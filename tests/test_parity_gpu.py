@@ -159,12 +159,72 @@ def test_systolic_lean_one_column_ragged_domains(domain, pml, zb):
 
 
 def test_systolic_lean_rejects_other_geometries():
-  kw = random_problem(domain=(8, 8, 64), tt=4, seed=1)
+  # neither 32 fp32 vectors per column (warp per column pair) nor <= 16 (half-warp variant)
+  kw = random_problem(domain=(8, 8, 72), tt=4, seed=1)
   with pytest.raises((ValueError, RuntimeError)):
     run_gpu(kw, kernel="systolic_lean")
-  kw = random_problem(domain=(8, 8, 128), tt=4, seed=1, reduced=True)
+  kw = random_problem(domain=(8, 8, 136), tt=4, seed=1, reduced=True)
   with pytest.raises((ValueError, RuntimeError)):
     run_gpu(kw, kernel="systolic_lean")
+
+
+# ---- half-warp variant of the lean kernel (kernels_lean16.cuh): columns of <= 16 vectors ---------
+
+@pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 128), (False, 64), (False, 30)])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (6, 3), (4, 40), (21, 2)])
+def test_systolic_lean_halfwarp_tilings(tile_y, stages, axis, reduced, Z):
+  """pjz's default engine geometry (fp16 storage, 96 z-cells) and its neighbours: every tiling,
+  all source orientations, bit-exact against the C oracle (fp16 storage mode included)."""
+  kw = random_problem(domain=(11, 23, Z), axis=axis, pml=(16, 16) if Z >= 64 else (5, 7), tt=45,
+                      seed=13, output_steps=(20, 45, 6), reduced=reduced)
+  want = fdtd_c.fdtdz(**kw)
+  out = run_gpu(kw, kernel="systolic_lean", tile_y=tile_y, stages=stages)
+  np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("reduced,domain,pml,zb", [
+    (True, (9, 14, 121), (3, 5), False), (True, (16, 1, 128), (0, 0), False),
+    (True, (5, 2, 127), (10, 12), False), (True, (12, 26, 96), (0, 0), True),
+    (True, (3, 30, 64), (16, 16), False), (True, (7, 9, 13), (3, 5), False),
+    (True, (6, 5, 1), (0, 0), False), (True, (2, 5, 8), (4, 4), False),
+    (False, (9, 14, 61), (3, 5), False), (False, (16, 1, 64), (0, 0), False),
+    (False, (5, 2, 63), (10, 12), False), (False, (12, 26, 32), (0, 0), True),
+    (False, (3, 30, 48), (16, 16), False), (False, (7, 9, 13), (3, 5), False),
+    (False, (6, 5, 1), (0, 0), False), (False, (2, 9, 8), (0, 3), False),
+    (False, (20, 47, 40), (5, 6), False), (True, (20, 47, 100), (12, 9), False)])
+def test_systolic_lean_halfwarp_ragged_domains(reduced, domain, pml, zb):
+  for axis in (0, 1, 2):
+    kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
+                        seed=7, output_steps=(5, 14, 4), absorb_pad=min(2, min(domain[:2]) // 2),
+                        z_as_batch=zb, reduced=reduced)
+    np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean"), fdtd_c.fdtdz(**kw))
+
+
+@pytest.mark.parametrize("reduced,Z", [(True, 96), (False, 64)])
+def test_systolic_lean_halfwarp_fused_projection(reduced, Z):
+  kw = random_problem(domain=(9, 21, Z), axis=0, pml=(8, 8), tt=33, seed=91, output_steps=(8, 33, 4),
+                      reduced=reduced)
+  W = np.random.default_rng(7).standard_normal((4, len(range(8, 33, 4)))).astype(np.float32)
+  want = fdtd_c.fdtdz(**kw, output_projection=W)
+  dev = dict(kw)
+  dev["launch_params"] = {"kernel": "systolic_lean"}
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  np.testing.assert_array_equal(fdtdz_jax.fdtdz(**dev, output_projection=W).cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 128), (False, 64)])
+def test_systolic_lean_halfwarp_long_run_at_pjz_default_size(reduced, Z):
+  """256x256 in x-y at pjz's default height, 300 steps through the full-size plan (L2 discard on
+  when a column is whole 128-byte lines): bit-for-bit against the cp.async kernel, which shares
+  neither the staging nor the discard logic; reduced precision within the stated bound of fp32."""
+  kw = random_problem(domain=(256, 256, Z), sub=(192, 192, Z - 32), offset=(32, 32, 16), axis=0,
+                      pml=(16, 16), tt=300, seed=6, output_steps=(120, 300, 89), absorb_pad=32,
+                      absorb_coeff=1e-4, reduced=reduced)
+  a = run_gpu(kw, kernel="systolic_async")
+  b = run_gpu(kw, kernel="systolic_lean")
+  np.testing.assert_array_equal(a, b)
+  assert np.isfinite(a).all() and np.abs(a[-1]).max() > 0
 
 
 @pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (5, 3), (14, 7), (4, 40)])

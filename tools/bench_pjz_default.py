@@ -19,14 +19,20 @@ def run(kw, reps=2, **lp):
   b.record(); torch.cuda.synchronize()
   return a.elapsed_time(b) / reps, fdtdz_jax.plan_info(**kw)
 
-for reduced, Z, pml in [(True, 96, (16, 16)), (False, 32, (16, 16)), (False, 48, (8, 8)), (True, 128, (16, 16))]:
+GEOMS = [(True, 96, (16, 16)), (False, 32, (16, 16)), (False, 48, (8, 8)), (True, 128, (16, 16)),
+         (False, 64, (8, 8))]
+VARIANTS = [dict(), dict(kernel="systolic_lean"), dict(kernel="systolic_async", cols=1),
+            dict(kernel="systolic_async", cols=2), dict(kernel="systolic"), dict(kernel="twopass")]
+if os.environ.get("QUICK"):      # half-warp lean kernel against the AUTO plan, plus its tilings
+  VARIANTS = [dict(), dict(kernel="systolic_async"), dict(kernel="systolic_lean")] + [
+      dict(kernel="systolic_lean", tile_y=t) for t in (19, 17, 15, 13, 11)]
+for reduced, Z, pml in GEOMS:
   X = Y = 256
   tt = 2000
   kw = random_problem(domain=(X, Y, Z), sub=(X - 64, Y - 64, max(Z - 8, 1)), offset=(32, 32, 4), axis=0,
                       pml=pml, tt=tt, seed=1, output_steps=(tt - 1, tt, 1), reduced=reduced,
                       absorb_pad=32, absorb_coeff=1e-4)
-  for lp in [dict(), dict(kernel="systolic_async", cols=1), dict(kernel="systolic_async", cols=2),
-             dict(kernel="systolic"), dict(kernel="twopass")]:
+  for lp in VARIANTS:
     ms, info = run(kw, **lp)
     if ms is None:
       print(json.dumps({"reduced": reduced, "Z": Z, "lp": lp, "error": info})); continue
