@@ -334,6 +334,8 @@ def main():
   if info["kernel"].startswith("systolic"):
     kname = {"systolic_lean": "lean_kernel", "systolic_async": "systolic2_kernel",
              "systolic_tma": "systolic3_kernel"}.get(info["kernel"], "systolic_kernel")
+    if info["kernel"] == "systolic_lean" and (args.reduced or dims[2] <= 64):
+      kname = "lean16_kernel"                    # sub-warp variant: columns of <= 16 vectors
     dominant = kname + " (1 launch per engine call; duration = call time incl. 3 prep kernels)"
     launches = (3 + 2) * args.steps
   else:

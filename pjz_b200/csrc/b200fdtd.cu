@@ -198,14 +198,18 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
     plan->depth = 1;
     return B200FDTD_OK;
   }
-  // fp16 storage with 13..16 vectors per column (97 <= Z <= 128): the half-warp lean kernel
-  // (measured 107 vs 85 Gcell/s on 256x256x128; with 12 vectors a quarter of its lanes idle and
-  // it only ties with the cp.async kernel: 80 vs 82).
-  if (d->kernel == B200FDTD_KERNEL_AUTO && sizeof(T) == 2 && g.Zq >= 13 && g.Zq <= kL16ZR &&
-      lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
-    plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
-    plan->depth = 1;
-    return B200FDTD_OK;
+  // Columns of at most 16 vectors (everything fdtd-z itself accepts): the sub-warp lean kernel
+  // where most of its lanes carry a vector.  Measured on 256x256 in x-y (Gcell/s, lean16 vs the
+  // cp.async kernel): fp16 Z=128 106 vs 85, fp16 Z=64 (8 lanes per column) 98 vs 80, fp32 Z=64
+  // 80 vs 73; with 12 of 16 lanes busy (fp16 Z=96) it only ties (78 vs 82), and fp32 columns of
+  // <= 8 vectors are slower (63 vs 70), so those stay on the cp.async kernel.
+  if (d->kernel == B200FDTD_KERNEL_AUTO && g.Zq <= kL16ZR) {
+    const bool wide = sizeof(T) == 2 ? ((g.Zq >= 13) || (g.Zq >= 7 && g.Zq <= 8)) : g.Zq >= 15;
+    if (wide && lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
+      plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
+      plan->depth = 1;
+      return B200FDTD_OK;
+    }
   }
   if (d->kernel == B200FDTD_KERNEL_AUTO || d->kernel == B200FDTD_KERNEL_SYSTOLIC_ASYNC) {
     const int depth = d->prefetch > 0 ? d->prefetch : 1;

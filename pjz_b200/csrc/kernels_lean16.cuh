@@ -1,54 +1,69 @@
-// "systolic_lean", half-warp generation: the warp-autonomous kernel of kernels_lean.cuh (read
-// that header first: same stage/tile decomposition, ping-pong buffers, progress protocol, service
-// warp and L2 discard rule) for z-columns of AT MOST 16 16-byte vectors -- fp16 storage with
-// Z <= 128 (pjz's default: use_reduced_precision=True, Z = 128 - sum(pml_widths) = 96,
-// /root/reference/src/pjz/_field.py:36,56-58) and fp32 storage with Z <= 64.
+// "systolic_lean", sub-warp generation: the warp-autonomous kernel of kernels_lean.cuh (read that
+// header first: same stage/tile decomposition, ping-pong buffers, progress protocol, service warp
+// and L2 discard rule) for z-columns of AT MOST 16 16-byte vectors -- everything fdtd-z itself
+// accepts: fp16 storage with Z <= 128 (pjz's default: use_reduced_precision=True,
+// Z = 128 - sum(pml_widths) = 96, /root/reference/src/pjz/_field.py:36,56-58) and fp32 storage
+// with Z <= 64.
 //
-//  * A warp still owns one PAIR of adjacent y-columns (tile-local 2w, 2w+1), but a thread owns
-//    ONE column: lanes 0..15 hold z-vectors 0..15 of column A, lanes 16..31 those of column B.
-//    With fp16 storage a vector is 8 cells, so a thread advances 8 cells per plane -- the same
-//    work per thread as the fp32 kernel's 2 columns x 4 cells -- from half the shared-memory
-//    reads and half the cp.async copies.
-//  * z+-1 neighbours are shuffles of width 16; x-1 is carried in registers along the sweep.
-//  * Each lane stages the operands of ITS column (E^n[P+1], H^{n-1/2}[P], B[P], psi[P]) into the
-//    per-warp cp.async ring.  The y+1 neighbour of column A is column B's ring row (read after
-//    cp.async.wait_group + __syncwarp); the column after the pair is copied once, Ex by the A
-//    lanes and Ez by the B lanes (one copy instruction per lane).
-//  * The y-1 neighbour (new Hz, Hx, already rounded to the storage type) goes through the 2-deep
-//    boundary slot: the A half of a warp's slot is read by its own B lanes (program order +
-//    __syncwarp), the B half by the A lanes of warp w+1 (produced / consumed counters).
-//  * Lanes q >= Zq (columns shorter than 16 vectors) run along on the addresses of lane Zq-1 and
-//    store nothing.
+//  * A z-column occupies LPC = 16 or 8 lanes (one 16-byte vector per lane), so a warp holds
+//    G = 32 / LPC sub-groups; a thread owns K adjacent columns (K = 1 for fp16 storage, where a
+//    vector is 8 cells; K = 2 for fp32, 4 cells per vector): 8 cells per thread and plane in both
+//    cases, the same work per thread as the fp32 kernel of kernels_lean.cuh.  A warp therefore
+//    owns CW = G * K adjacent columns, tile-local CW*w .. CW*w + CW - 1 (column 0 = y0-1 halo).
+//  * z+-1 neighbours are shuffles of width LPC; x-1 is carried in registers along the sweep; the
+//    y neighbour inside a thread's K columns is its own registers.
+//  * Each lane stages the operands of ITS columns (E^n[P+1], H^{n-1/2}[P], B[P], psi[P]) into the
+//    per-warp cp.async ring.  The y+1 neighbour of a sub-group's last column is the next
+//    sub-group's ring row (read after cp.async.wait_group + __syncwarp); the column after the
+//    warp's last one is copied once, Ex by sub-group 0 and Ez by sub-group 1.
+//  * The y-1 neighbour of a sub-group's first column (new Hz, Hx, already rounded to the storage
+//    type) goes through the 2-deep boundary slot: sub-group h reads what sub-group h-1 wrote
+//    (program order + __syncwarp); sub-group 0 reads the last sub-group of warp w-1
+//    (produced / consumed counters, as in kernels_lean.cuh).
+//  * Lanes q >= Zq (columns shorter than LPC vectors) run along on the addresses of lane Zq-1
+//    and store nothing; columns beyond the tile's E-only column Yt+1 are clamped onto it.
 //  * CPML tables: registers for fp32 (24 values), shared memory for fp16 (48 values would not fit
 //    next to the 8-cell working set under the 168-register cap of 12 warps).
-//  * L2 discard needs whole 128-byte lines per column: only when Zq is a multiple of 8.
+//  * L2 discard needs whole 128-byte lines per column (Zq a multiple of 8) and is opt-in here
+//    (B200FDTD_LEAN_DISCARD=1): it halves HBM traffic but costs 4-5 % throughput at these sizes.
 #pragma once
 
 #include "kernels_lean.cuh"
 
 namespace b200 {
 
-constexpr int kL16MaxWarps = 11;       // compute warps per CTA (+1 service warp: 384 threads)
-constexpr int kL16ZR = 16;             // lanes (16-byte vectors) per z-column / ring row
-constexpr int kL16ERows = 8;           // rows per E slot: Ex[A,B,C], Ez[A,B,C], Ey[A,B]
-constexpr int kL16HRows = 12;          // rows per H/B slot: Hx,Hy,Hz[A,B], Bx,By,Bz[A,B]
+constexpr int kL16ZR = 16;             // most 16-byte vectors per z-column this kernel takes
+
+template <typename T, int LPC, int K>
+struct L16 {
+  static constexpr int VW = VecTraits<T>::VW;
+  static constexpr int PV = VW / 4;              // float4 per psi / table vector
+  static constexpr int G = 32 / LPC;             // sub-groups (column slices) per warp
+  static constexpr int CW = G * K;               // columns per warp
+  static constexpr int ERows = 3 * CW + 2;       // Ex[0..CW], Ez[0..CW], Ey[0..CW-1]
+  static constexpr int HRows = 6 * CW;           // Hx, Hy, Hz, Bx, By, Bz [0..CW-1]
+  static constexpr int XF4 = G * 2 * LPC;        // float4 per boundary-slot ring entry (= 64)
+  static constexpr int MaxWarps = K == 2 ? 8 : 11;   // compute warps per CTA (+1 service warp)
+  static size_t eslot_f4() { return (size_t)ERows * LPC; }
+  static size_t hslot_f4(int npg) { return (size_t)HRows * LPC + 4 * CW * (size_t)npg * PV + 2 * CW; }
+  static size_t warp_f4(int npg) { return 3 * eslot_f4() + 2 * hslot_f4(npg) + (size_t)kLeanXR * XF4; }
+};
 
 struct Lean16Ctl {
   unsigned avail, next, ok, front, exited;   // as LeanCtl
-  unsigned wdone[kL16MaxWarps + 1];
-  unsigned hcnt[kL16MaxWarps + 1];
-  unsigned rcnt[kL16MaxWarps + 1];
+  unsigned wdone[12];
+  unsigned hcnt[12];
+  unsigned rcnt[12];
 };
 
-template <typename T>
-__global__ void __launch_bounds__(32 * (kL16MaxWarps + 1), 1)
+template <typename T, int LPC, int K>
+__global__ void __launch_bounds__(32 * (L16<T, LPC, K>::MaxWarps + 1), 1)
 lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sync) {
-  constexpr int VW = VecTraits<T>::VW;
-  constexpr int PV = VW / 4;                       // float4 per psi / table vector
-  constexpr int ZR = kL16ZR;
+  using C = L16<T, LPC, K>;
+  constexpr int VW = C::VW, PV = C::PV, G = C::G, CW = C::CW;
   extern __shared__ float4 smem[];
   __shared__ Lean16Ctl ctl;
-  __shared__ float4 stab[6][ZR * PV];              // CPML tables, [table][lane * PV + k]
+  __shared__ float4 stab[6][PV * LPC];             // CPML tables, [table][part * LPC + lane]
   const int tid = threadIdx.x, lane = tid & 31;
   const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
@@ -56,21 +71,21 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   const int t = blockIdx.x % NT, j = blockIdx.x / NT;
   const int y0 = (int)((long long)t * g.Y / NT);
   const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
-  const int X = g.X, Y = g.Y, Zq = g.Zq;
-  const int psi_row = g.npg * PV;                  // float4 per psi row of a slot
-  const int eslot_f4 = kL16ERows * ZR;
-  const int hslot_f4 = kL16HRows * ZR + 8 * psi_row + 4;   // + 8 psi rows, 2 absorber, 2 z-source rows
-  const int warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + kLeanXR * 4 * ZR;
-  const int NWt = min(NW, (Yt + 2) / 2);           // warps with work on THIS tile (balanced tiles)
+  const int X = g.X, Y = g.Y, Zq = g.Zq, npg = g.npg;
+  const int psi_row = npg * PV;                    // float4 per psi row of a slot
+  const int eslot_f4 = C::ERows * LPC;
+  const int hslot_f4 = C::HRows * LPC + 4 * CW * psi_row + 2 * CW;   // + psi rows, absorber, z-source rows
+  const int warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + kLeanXR * C::XF4;
+  const int NWt = min(NW, (Yt + CW) / CW);         // warps with an H-forming column on THIS tile
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
 
   if (tid < (int)(sizeof(Lean16Ctl) / sizeof(unsigned))) reinterpret_cast<unsigned*>(&ctl)[tid] = 0u;
-  for (int i = tid; i < 6 * ZR * PV; i += (int)blockDim.x) {
-    const int k = i / (ZR * PV), r = i % (ZR * PV);
-    stab[k][r] = r < Zq * PV ? __ldg(reinterpret_cast<const float4*>(p.tab + (size_t)k * g.Zp) + r)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 6 * PV * LPC; i += (int)blockDim.x) {
+    const int k = i / (PV * LPC), r = i % (PV * LPC), part = r / LPC, ql = r % LPC;
+    stab[k][r] = ql < Zq ? __ldg(reinterpret_cast<const float4*>(p.tab + (size_t)k * g.Zp) + ql * PV + part)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   if (tid == 0) ctl.ok = 1u;
@@ -147,30 +162,40 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
     if (lane == 0) atomicAdd(&ctl.exited, 1u);
     return;
   }
-  const int h = lane >> 4, q = lane & (ZR - 1);    // half (0: column A, 1: column B), z-vector
+  const int h = lane / LPC, q = lane % LPC;        // sub-group (column slice), z-vector
   const bool live = q < Zq;
   const int qc = live ? q : Zq - 1;                // addresses of a lane beyond the column's top
-  const int c = 2 * w + h;                         // tile-local column; 0 is the y0-1 halo
-  const bool own = c >= 1 && c <= Yt && live;      // E-updated and stored by this lane
-  const bool doHB = 2 * w + 1 <= Yt;               // column B forms H (warp-uniform)
-  const int y = wrapi(y0 - 1 + c, Y);
-  const int yC = wrapi(y0 - 1 + (doHB ? 2 * w + 2 : 2 * w + 1), Y);
-  const unsigned PVn = (unsigned)Y * Zq;           // vectors per x-plane
-  const unsigned tv = (unsigned)y * Zq + qc, tvC = (unsigned)yC * Zq + qc;
   const int slot = psi_slot(g, qc);
   const bool has_psi = live && slot >= 0;
+  const unsigned PVn = (unsigned)Y * Zq;           // vectors per x-plane
   const unsigned PPn = (unsigned)Y * psi_row;      // psi float4 per x-plane
-  const unsigned pv = ((unsigned)y * g.npg + (has_psi ? slot : 0)) * PV;
+  const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : Y);
+  int yk[K];                                       // tile-local column CW*w + K*h + k; 0 = y0-1 halo
+  unsigned tv[K], pv[K];
+  bool own[K], disc[K], srcY[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int c = CW * w + K * h + k;
+    yk[k] = wrapi(y0 - 1 + min(c, Yt + 1), Y);
+    own[k] = live && c >= 1 && c <= Yt;            // E-updated and stored by this lane
+    disc[k] = cfg.discard && live && (q & 7) == 0 && c >= 2 && c <= Yt - 1;
+    srcY[k] = g.src_axis == 1 && (yk[k] == sp0 || yk[k] == sp1);
+    tv[k] = (unsigned)yk[k] * Zq + qc;
+    pv[k] = ((unsigned)yk[k] * npg + (has_psi ? slot : 0)) * PV;
+  }
+  const int yC = wrapi(y0 - 1 + min(CW * w + CW, Yt + 1), Y);     // the column after the warp's last
+  const unsigned tvC = (unsigned)yC * Zq + qc;
+  const int ya = (K == 2 && (q & 1)) ? yk[K - 1] : yk[0];   // column whose absorber / z-source row lane q copies
   const bool top = q + 1 >= Zq, bottom = q == 0;
-  const bool disc = cfg.discard && live && (q & 7) == 0 && c >= 2 && c <= Yt - 1;
 
   float4* const wbase = smem + (size_t)w * warp_f4;
   float4* const hbase = wbase + 3 * eslot_f4;
   float4* const xbase = hbase + 2 * hslot_f4;                     // boundary-H slots of this warp
-  float4* const xmine = xbase + h * 2 * ZR + q;
-  // (Hz, Hx) of column c-1: the A half of this warp's slot for the B lanes, the B half of warp
-  // w-1's slot for the A lanes (column 0 has no predecessor and is never E-updated)
-  const float4* const xread = h ? xbase + q : (w > 0 ? xbase - warp_f4 + 2 * ZR + q : xbase + q);
+  float4* const xmine = xbase + h * 2 * LPC + q;
+  // (Hz, Hx) of the column before this sub-group's first: sub-group h-1 of this warp, or the last
+  // sub-group of warp w-1 (column 0 has no predecessor and is never E-updated)
+  const float4* const xread = h > 0 ? xbase + (h - 1) * 2 * LPC + q
+                                    : (w > 0 ? xbase - warp_f4 + (G - 1) * 2 * LPC + q : xbase + q);
 
   // CPML tables: registers when they are 4 values each
   float tabr[6][4];
@@ -185,15 +210,16 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
     } else {
 #pragma unroll
       for (int i = 0; i < PV; ++i) {
-        const float4 r = stab[k][q * PV + i];
+        const float4 r = stab[k][i * LPC + q];
         v[4 * i] = r.x; v[4 * i + 1] = r.y; v[4 * i + 2] = r.z; v[4 * i + 3] = r.w;
       }
     }
   };
+  // psi vectors of a column in a ring row: part i of PML group `slot` at [i * npg + slot]
   auto load_psi = [&](const float4* ps, float (&v)[VW]) {
 #pragma unroll
     for (int i = 0; i < PV; ++i) {
-      const float4 r = ps[i];
+      const float4 r = ps[i * npg];
       v[4 * i] = r.x; v[4 * i + 1] = r.y; v[4 * i + 2] = r.z; v[4 * i + 3] = r.w;
     }
   };
@@ -203,9 +229,6 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       __stcg(dst + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
   };
 
-  // plane source: cheap pre-tests so that add_source() stays off the common path
-  const int sp0 = g.src_pos, sp1 = wrapi(g.src_pos - 1, g.src_axis == 0 ? X : Y);
-  const bool srcY = g.src_axis == 1 && (y == sp0 || y == sp1);
   const float dt = g.dt;
   const float4* const A4 = reinterpret_cast<const float4*>(p.A4);
   const float4* const S4 = reinterpret_cast<const float4*>(p.S4);
@@ -249,7 +272,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
     const float4* const rEx = reinterpret_cast<const float4*>(p.Es[rb][0]);
     const float4* const rEy = reinterpret_cast<const float4*>(p.Es[rb][1]);
     const float4* const rEz = reinterpret_cast<const float4*>(p.Es[rb][2]);
-    const float4* const rEc = h ? rEz : rEx;       // this lane's share of the column after the pair
+    const float4* const rEc = h ? rEz : rEx;       // this lane's share of the column after the warp's
     const float4* const rHx = reinterpret_cast<const float4*>(p.Hs[rb][0]);
     const float4* const rHy = reinterpret_cast<const float4*>(p.Hs[rb][1]);
     const float4* const rHz = reinterpret_cast<const float4*>(p.Hs[rb][2]);
@@ -278,41 +301,51 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
     };
 
     // Async copies of one iteration (plane PL): E[PL+1] -> E slot se; H, B, psi, absorber row of
-    // PL -> H/B slot sh.  Straight-line: halo / E-only columns are copied all the same.
+    // PL -> H/B slot sh.  Straight-line: halo / E-only / clamped columns are copied all the same.
     auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first) {
       const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
-      float4* const d = se + h * ZR + q;
-      float4* const hh = sh + h * ZR + q;
-      cp_async16(d + 0 * ZR, rEx + (vN + tv));
-      cp_async16(d + 3 * ZR, rEz + (vN + tv));
-      cp_async16(d + 6 * ZR, rEy + (vN + tv));
-      cp_async16(se + (h ? 5 : 2) * ZR + q, rEc + (vN + tvC));
-      cp_async16(hh + 0 * ZR, rHx + (vP + tv));
-      cp_async16(hh + 2 * ZR, rHy + (vP + tv));
-      cp_async16(hh + 4 * ZR, rHz + (vP + tv));
-      cp_async16(hh + 6 * ZR, Bx + (vP + tv));
-      cp_async16(hh + 8 * ZR, By + (vP + tv));
-      cp_async16(hh + 10 * ZR, Bz + (vP + tv));
-      float4* const tail = sh + kL16HRows * ZR + 8 * psi_row;
-      if (q == 0) cp_async16(tail + h, A4 + ((unsigned)PL * (unsigned)Y + y));
-      if (zsrc && q == 1) cp_async16(tail + 2 + h, S4 + ((unsigned)PL * (unsigned)Y + y));
-      if (has_psi) {
-        float4* const ps = sh + kL16HRows * ZR + h * psi_row + slot * PV;
-        const unsigned pp = (unsigned)PL * PPn + pv;
 #pragma unroll
-        for (int k = 0; k < PV; ++k) {
-          cp_async16(ps + 0 * psi_row + k, rPx + (pp + k));
-          cp_async16(ps + 2 * psi_row + k, rPy + (pp + k));
-          cp_async16(ps + 4 * psi_row + k, ePx + (pp + k));
-          cp_async16(ps + 6 * psi_row + k, ePy + (pp + k));
+      for (int k = 0; k < K; ++k) {
+        float4* const d = se + (K * h + k) * LPC + q;
+        float4* const hh = sh + (K * h + k) * LPC + q;
+        cp_async16(d, rEx + (vN + tv[k]));
+        cp_async16(d + (CW + 1) * LPC, rEz + (vN + tv[k]));
+        cp_async16(d + 2 * (CW + 1) * LPC, rEy + (vN + tv[k]));
+        cp_async16(hh + 0 * CW * LPC, rHx + (vP + tv[k]));
+        cp_async16(hh + 1 * CW * LPC, rHy + (vP + tv[k]));
+        cp_async16(hh + 2 * CW * LPC, rHz + (vP + tv[k]));
+        cp_async16(hh + 3 * CW * LPC, Bx + (vP + tv[k]));
+        cp_async16(hh + 4 * CW * LPC, By + (vP + tv[k]));
+        cp_async16(hh + 5 * CW * LPC, Bz + (vP + tv[k]));
+      }
+      if (G == 2 || h < 2) cp_async16(se + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vN + tvC));
+      float4* const tail = sh + C::HRows * LPC + 4 * CW * psi_row;
+      if (q < K) cp_async16(tail + K * h + q, A4 + ((unsigned)PL * (unsigned)Y + ya));
+      if (zsrc && q >= K && q < 2 * K)
+        cp_async16(tail + CW + K * h + (q - K), S4 + ((unsigned)PL * (unsigned)Y + ya));
+      if (has_psi) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float4* const ps = sh + C::HRows * LPC + (K * h + k) * psi_row + slot;
+          const unsigned pp = (unsigned)PL * PPn + pv[k];
+#pragma unroll
+          for (int i = 0; i < PV; ++i) {
+            cp_async16(ps + 0 * CW * psi_row + i * npg, rPx + (pp + i));
+            cp_async16(ps + 1 * CW * psi_row + i * npg, rPy + (pp + i));
+            cp_async16(ps + 2 * CW * psi_row + i * npg, ePx + (pp + i));
+            cp_async16(ps + 3 * CW * psi_row + i * npg, ePy + (pp + i));
+          }
         }
       }
       if (se_first) {                                // very first plane of the sweep: E[PL] too
-        float4* const f = se_first + h * ZR + q;
-        cp_async16(f + 0 * ZR, rEx + (vP + tv));
-        cp_async16(f + 3 * ZR, rEz + (vP + tv));
-        cp_async16(f + 6 * ZR, rEy + (vP + tv));
-        cp_async16(se_first + (h ? 5 : 2) * ZR + q, rEc + (vP + tvC));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float4* const f = se_first + (K * h + k) * LPC + q;
+          cp_async16(f, rEx + (vP + tv[k]));
+          cp_async16(f + (CW + 1) * LPC, rEz + (vP + tv[k]));
+          cp_async16(f + 2 * (CW + 1) * LPC, rEy + (vP + tv[k]));
+        }
+        if (G == 2 || h < 2) cp_async16(se_first + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vP + tvC));
       }
     };
 
@@ -327,9 +360,11 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
     if (ok) issue(P, P + 1 == X ? 0 : P + 1, scur, hcur, sprev);
     cp_async_commit();
 
-    float hyp[VW], hzp[VW];                        // H^{n+1/2}[P-1] of the thread's own cells
+    float hyp[K][VW], hzp[K][VW];                  // H^{n+1/2}[P-1] of the thread's own cells
 #pragma unroll
-    for (int v = 0; v < VW; ++v) { hyp[v] = 0.f; hzp[v] = 0.f; }
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int v = 0; v < VW; ++v) { hyp[k][v] = 0.f; hzp[k][v] = 0.f; }
 
     for (int i = 0; i <= X && ok; ++i) {
       const bool real = i >= 1;
@@ -344,59 +379,80 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       cp_async_commit();
       __syncwarp();                                // ... and so have those of the other lanes
       if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
-      // Dead lines (see kernels_lean.cuh): Ey and H of both columns and (Ex, Ez) of column B have
-      // been read by their only reader; (Ex, Ez) of column A wait for warp w-1 (E half-step).
-      if (disc && i >= 1) {
+      // Dead lines (see kernels_lean.cuh): Ey and H of every column and (Ex, Ez) of every column
+      // but the warp's first have been read by their only reader; (Ex, Ez) of the warp's first
+      // column wait for warp w-1 (E half-step).
+      if (i >= 1) {
         const unsigned vN = (unsigned)Pn * PVn;
-        discard_l2_line(rEy + (vN + tv));
-        discard_l2_line(rHx + (vP + tv)); discard_l2_line(rHy + (vP + tv));
-        discard_l2_line(rHz + (vP + tv));
-        if (h) { discard_l2_line(rEx + (vN + tv)); discard_l2_line(rEz + (vN + tv)); }
-      }
-
-      const unsigned pP = (unsigned)P * PPn + pv;
-
-      // ---------------------------------- H half-step ---------------------------------------------
-      const float4* const ep = sprev + h * ZR + q;
-      const float4* const ec = scur + h * ZR + q;
-      const float4* const hc = hcur + h * ZR + q;
-      const float4* const pc = hcur + kL16HRows * ZR + h * psi_row + (has_psi ? slot : 0) * PV;
-      const float4* const tail = hcur + kL16HRows * ZR + 8 * psi_row;
-      float ex[VW], ey[VW], ez[VW], hx[VW], hy[VW], hz[VW], psx[VW], psy[VW];
-      {
-        float exy[VW], ezy[VW], eyx[VW], ezx[VW], ah[VW], bh[VW], ikh[VW];
-        unpack(lds16(ep + 0 * ZR), ex, T()); unpack(lds16(ep + 3 * ZR), ez, T());
-        unpack(lds16(ep + 6 * ZR), ey, T());
-        unpack(lds16(ep + 1 * ZR), exy, T()); unpack(lds16(ep + 4 * ZR), ezy, T());
-        unpack(lds16(ec + 6 * ZR), eyx, T()); unpack(lds16(ec + 3 * ZR), ezx, T());
-        unpack(lds16(hc + 0 * ZR), hx, T()); unpack(lds16(hc + 2 * ZR), hy, T());
-        unpack(lds16(hc + 4 * ZR), hz, T());
 #pragma unroll
-        for (int v = 0; v < VW; ++v) { psx[v] = 0.f; psy[v] = 0.f; }
-        if (has_psi) { load_psi(pc, psx); load_psi(pc + 2 * psi_row, psy); }
-        load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
-        float ex_top = __shfl_down_sync(0xffffffffu, ex[0], 1, ZR);
-        float ey_top = __shfl_down_sync(0xffffffffu, ey[0], 1, ZR);
-        if (top) { ex_top = 0.f; ey_top = 0.f; }
-#pragma unroll
-        for (int v = 0; v < VW; ++v) {
-          const float exz = (v + 1 < VW) ? ex[(v + 1) % VW] : ex_top;
-          const float eyz = (v + 1 < VW) ? ey[(v + 1) % VW] : ey_top;
-          h_cell(ex[v], ey[v], ez[v], exz, eyz, ezy[v], exy[v], eyx[v], ezx[v], ah[v], bh[v],
-                 ikh[v], dt, psx[v], psy[v], hx[v], hy[v], hz[v]);
-          hx[v] = round_store<T>(hx[v]); hy[v] = round_store<T>(hy[v]); hz[v] = round_store<T>(hz[v]);
+        for (int k = 0; k < K; ++k) {
+          if (disc[k]) {
+            discard_l2_line(rEy + (vN + tv[k]));
+            discard_l2_line(rHx + (vP + tv[k])); discard_l2_line(rHy + (vP + tv[k]));
+            discard_l2_line(rHz + (vP + tv[k]));
+            if (k > 0 || h > 0) { discard_l2_line(rEx + (vN + tv[k])); discard_l2_line(rEz + (vN + tv[k])); }
+          }
         }
       }
-      // boundary H for the next column: the B half waits until warp w+1 has consumed the slot
+
+      // ---------------------------------- H half-step ---------------------------------------------
+      const float4* const ep = sprev + K * h * LPC + q;
+      const float4* const ec = scur + K * h * LPC + q;
+      const float4* const hc = hcur + K * h * LPC + q;
+      const float4* const pc = hcur + C::HRows * LPC + K * h * psi_row + (has_psi ? slot : 0);
+      const float4* const tail = hcur + C::HRows * LPC + 4 * CW * psi_row;
+      float ex[K][VW], ey[K][VW], ez[K][VW], hx[K][VW], hy[K][VW], hz[K][VW], psx[K][VW], psy[K][VW];
       {
-        float4* const xs = xmine + (kk & (kLeanXR - 1)) * 4 * ZR;
+        float exn[VW], ezn[VW], ah[VW], bh[VW], ikh[VW];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          unpack(lds16(ep + k * LPC), ex[k], T());
+          unpack(lds16(ep + (CW + 1 + k) * LPC), ez[k], T());
+          unpack(lds16(ep + (2 * (CW + 1) + k) * LPC), ey[k], T());
+          unpack(lds16(hc + (0 * CW + k) * LPC), hx[k], T());
+          unpack(lds16(hc + (1 * CW + k) * LPC), hy[k], T());
+          unpack(lds16(hc + (2 * CW + k) * LPC), hz[k], T());
+#pragma unroll
+          for (int v = 0; v < VW; ++v) { psx[k][v] = 0.f; psy[k][v] = 0.f; }
+          if (has_psi) {
+            load_psi(pc + (0 * CW + k) * psi_row, psx[k]);
+            load_psi(pc + (1 * CW + k) * psi_row, psy[k]);
+          }
+        }
+        unpack(lds16(ep + K * LPC), exn, T());                 // the column after this thread's last
+        unpack(lds16(ep + (CW + 1 + K) * LPC), ezn, T());
+        load_tab(3, ah); load_tab(4, bh); load_tab(5, ikh);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float eyx[VW], ezx[VW];
+          unpack(lds16(ec + (2 * (CW + 1) + k) * LPC), eyx, T());
+          unpack(lds16(ec + (CW + 1 + k) * LPC), ezx, T());
+          float ex_top = __shfl_down_sync(0xffffffffu, ex[k][0], 1, LPC);
+          float ey_top = __shfl_down_sync(0xffffffffu, ey[k][0], 1, LPC);
+          if (top) { ex_top = 0.f; ey_top = 0.f; }
+#pragma unroll
+          for (int v = 0; v < VW; ++v) {
+            const float exz = (v + 1 < VW) ? ex[k][(v + 1) % VW] : ex_top;
+            const float eyz = (v + 1 < VW) ? ey[k][(v + 1) % VW] : ey_top;
+            const float ez_yp = (k + 1 < K) ? ez[(k + 1) % K][v] : ezn[v];
+            const float ex_yp = (k + 1 < K) ? ex[(k + 1) % K][v] : exn[v];
+            h_cell(ex[k][v], ey[k][v], ez[k][v], exz, eyz, ez_yp, ex_yp, eyx[v], ezx[v], ah[v], bh[v],
+                   ikh[v], dt, psx[k][v], psy[k][v], hx[k][v], hy[k][v], hz[k][v]);
+            hx[k][v] = round_store<T>(hx[k][v]); hy[k][v] = round_store<T>(hy[k][v]);
+            hz[k][v] = round_store<T>(hz[k][v]);
+          }
+        }
+      }
+      // boundary H for the next column: the last sub-group waits until warp w+1 has consumed the slot
+      {
+        float4* const xs = xmine + (kk & (kLeanXR - 1)) * C::XF4;
         if (kk >= (unsigned)kLeanXR && w + 1 < NWt) {
           const unsigned need = kk + 1u - (unsigned)kLeanXR;
           ok = spin([&]() { return ld_vol_s(&ctl.rcnt[w]) >= need; });
           if (!ok) break;
         }
-        xs[0] = pack(hz, T());
-        xs[ZR] = pack(hx, T());
+        xs[0] = pack(hz[K - 1], T());
+        xs[LPC] = pack(hx[K - 1], T());
         __syncwarp();
         if (lane == 0) st_vol_s(&ctl.hcnt[w], kk + 1u);
       }
@@ -408,67 +464,81 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
           ok = spin([&]() { return ld_vol_s(&ctl.hcnt[w - 1]) >= need; });
           if (!ok) break;
         }
-        float hzm[VW], hxm[VW];                    // (Hz, Hx) of column c-1
+        float hzm[VW], hxm[VW];                    // (Hz, Hx) of the column before this thread's first
         {
-          const float4* const xr = xread + (kk & (kLeanXR - 1)) * 4 * ZR;
-          unpack(lds16(xr), hzm, T()); unpack(lds16(xr + ZR), hxm, T());
+          const float4* const xr = xread + (kk & (kLeanXR - 1)) * C::XF4;
+          unpack(lds16(xr), hzm, T()); unpack(lds16(xr + LPC), hxm, T());
         }
         __syncwarp();
         if (w > 0) {
           if (lane == 0) st_vol_s(&ctl.rcnt[w - 1], kk + 1u);
-          // warp w-1 has finished the H half-step of this iteration: its copy of column A's
-          // (Ex, Ez)[P+1] -- the only other reader -- has landed
-          if (disc && !h) {
+          // warp w-1 has finished the H half-step of this iteration: its copy of (Ex, Ez)[P+1] of
+          // this warp's first column -- the only other reader -- has landed
+          if (disc[0] && h == 0) {
             const unsigned vN = (unsigned)Pn * PVn;
-            discard_l2_line(rEx + (vN + tv)); discard_l2_line(rEz + (vN + tv));
+            discard_l2_line(rEx + (vN + tv[0])); discard_l2_line(rEz + (vN + tv[0]));
           }
         }
-        float hx_bot = __shfl_up_sync(0xffffffffu, hx[VW - 1], 1, ZR);
-        float hy_bot = __shfl_up_sync(0xffffffffu, hy[VW - 1], 1, ZR);
-        if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
-        if (own) {
-          float b0[VW], b1[VW], b2[VW], qsx[VW], qsy[VW], ae[VW], be[VW], ike[VW];
-          unpack(lds16(hc + 6 * ZR), b0, T()); unpack(lds16(hc + 8 * ZR), b1, T());
-          unpack(lds16(hc + 10 * ZR), b2, T());
-          const float4 aa = lds16(tail + h);
+        float ae[VW], be[VW], ike[VW];
+        load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
 #pragma unroll
-          for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
-          if (has_psi) { load_psi(pc + 4 * psi_row, qsx); load_psi(pc + 6 * psi_row, qsy); }
-          load_tab(0, ae); load_tab(1, be); load_tab(2, ike);
+        for (int k = 0; k < K; ++k) {
+          float hx_bot = __shfl_up_sync(0xffffffffu, hx[k][VW - 1], 1, LPC);
+          float hy_bot = __shfl_up_sync(0xffffffffu, hy[k][VW - 1], 1, LPC);
+          if (bottom) { hx_bot = 0.f; hy_bot = 0.f; }
+          if (own[k]) {
+            float b0[VW], b1[VW], b2[VW], qsx[VW], qsy[VW];
+            unpack(lds16(hc + (3 * CW + k) * LPC), b0, T()); unpack(lds16(hc + (4 * CW + k) * LPC), b1, T());
+            unpack(lds16(hc + (5 * CW + k) * LPC), b2, T());
+            const float4 aa = lds16(tail + K * h + k);
 #pragma unroll
-          for (int v = 0; v < VW; ++v) {
-            const float hxz = (v > 0) ? hx[(v + VW - 1) % VW] : hx_bot;
-            const float hyz = (v > 0) ? hy[(v + VW - 1) % VW] : hy_bot;
-            e_cell(hx[v], hy[v], hz[v], hxz, hyz, hzm[v], hxm[v], hyp[v], hzp[v], ae[v], be[v],
-                   ike[v], aa.x, aa.y, aa.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], ex[v], ey[v], ez[v]);
-          }
-          if (zsrc) {
-            // z-plane source: same operation order as add_source() (channel 0, then 1)
-            const float4 s = lds16(tail + 2 + h);
+            for (int v = 0; v < VW; ++v) { qsx[v] = 0.f; qsy[v] = 0.f; }
+            if (has_psi) {
+              load_psi(pc + (2 * CW + k) * psi_row, qsx);
+              load_psi(pc + (3 * CW + k) * psi_row, qsy);
+            }
 #pragma unroll
             for (int v = 0; v < VW; ++v) {
-              const float t0 = fmaf(w1, s.z, fmaf(w0, s.x, ex[v]));
-              const float t1 = fmaf(w1, s.w, fmaf(w0, s.y, ey[v]));
-              const bool hit = zhit && v == zidx;
-              ex[v] = hit ? t0 : ex[v];
-              ey[v] = hit ? t1 : ey[v];
+              const float hxz = (v > 0) ? hx[k][(v + VW - 1) % VW] : hx_bot;
+              const float hyz = (v > 0) ? hy[k][(v + VW - 1) % VW] : hy_bot;
+              const float hz_ym = (k > 0) ? hz[(k + K - 1) % K][v] : hzm[v];
+              const float hx_ym = (k > 0) ? hx[(k + K - 1) % K][v] : hxm[v];
+              e_cell(hx[k][v], hy[k][v], hz[k][v], hxz, hyz, hz_ym, hx_ym, hyp[k][v], hzp[k][v], ae[v],
+                     be[v], ike[v], aa.x, aa.y, aa.z, b0[v], b1[v], b2[v], qsx[v], qsy[v], ex[k][v],
+                     ey[k][v], ez[k][v]);
             }
-          } else if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcY) {
-            add_source<VW>(g, p.src, w0, w1, P, y, q, ex, ey, ez);
-          }
-          const unsigned o = vP + tv;
-          __stcg(wHx + o, pack(hx, T())); __stcg(wHy + o, pack(hy, T())); __stcg(wHz + o, pack(hz, T()));
-          __stcg(wEx + o, pack(ex, T())); __stcg(wEy + o, pack(ey, T())); __stcg(wEz + o, pack(ez, T()));
-          if (has_psi) {
-            store_psi(wPx + pP, psx); store_psi(wPy + pP, psy);
-            store_psi(ePx + pP, qsx); store_psi(ePy + pP, qsy);
-          }
-          if (oi >= 0) {
+            if (zsrc) {
+              // z-plane source: same operation order as add_source() (channel 0, then 1)
+              const float4 s = lds16(tail + CW + K * h + k);
 #pragma unroll
-            for (int v = 0; v < VW; ++v) {
-              ex[v] = round_store<T>(ex[v]); ey[v] = round_store<T>(ey[v]); ez[v] = round_store<T>(ez[v]);
+              for (int v = 0; v < VW; ++v) {
+                const float t0 = fmaf(w1, s.z, fmaf(w0, s.x, ex[k][v]));
+                const float t1 = fmaf(w1, s.w, fmaf(w0, s.y, ey[k][v]));
+                const bool hit = zhit && v == zidx;
+                ex[k][v] = hit ? t0 : ex[k][v];
+                ey[k][v] = hit ? t1 : ey[k][v];
+              }
+            } else if (g.src_axis == 0 ? (P == sp0 || P == sp1) : srcY[k]) {
+              add_source<VW>(g, p.src, w0, w1, P, yk[k], q, ex[k], ey[k], ez[k]);
             }
-            write_snapshot<VW>(g, p.out, oi, P, y, q, ex, ey, ez, p.proj);
+            const unsigned o = vP + tv[k];
+            __stcg(wHx + o, pack(hx[k], T())); __stcg(wHy + o, pack(hy[k], T()));
+            __stcg(wHz + o, pack(hz[k], T()));
+            __stcg(wEx + o, pack(ex[k], T())); __stcg(wEy + o, pack(ey[k], T()));
+            __stcg(wEz + o, pack(ez[k], T()));
+            if (has_psi) {
+              const unsigned pP = (unsigned)P * PPn + pv[k];
+              store_psi(wPx + pP, psx[k]); store_psi(wPy + pP, psy[k]);
+              store_psi(ePx + pP, qsx); store_psi(ePy + pP, qsy);
+            }
+            if (oi >= 0) {
+#pragma unroll
+              for (int v = 0; v < VW; ++v) {
+                ex[k][v] = round_store<T>(ex[k][v]); ey[k][v] = round_store<T>(ey[k][v]);
+                ez[k][v] = round_store<T>(ez[k][v]);
+              }
+              write_snapshot<VW>(g, p.out, oi, P, yk[k], q, ex[k], ey[k], ez[k], p.proj);
+            }
           }
         }
         // every store of sweep indices <= i has been issued by this warp
@@ -481,7 +551,9 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
         st_vol_s(&ctl.rcnt[w - 1], kk + 1u);       // prologue plane: nothing to consume
       }
 #pragma unroll
-      for (int v = 0; v < VW; ++v) { hyp[v] = hy[v]; hzp[v] = hz[v]; }
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int v = 0; v < VW; ++v) { hyp[k][v] = hy[k][v]; hzp[k][v] = hz[k][v]; }
       P = Pn;
       float4* const tmp = sprev; sprev = scur; scur = snext; snext = tmp;
       float4* const tmh = hcur; hcur = hnext; hnext = tmh;
@@ -495,41 +567,40 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
 }
 
-// Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.
-inline int lean16_warps(int tile_y) { return (tile_y + 2) / 2; }
+// Which instance serves a geometry: K = 2 columns per thread for fp32 (4 cells per vector), 1 for
+// fp16 (8 cells per vector); 8 lanes per column when the column has at most 8 vectors.
+template <typename T> constexpr int l16_k() { return sizeof(T) == 4 ? 2 : 1; }
 
-inline size_t lean16_smem_bytes(const Geom& g, int vw, int tile_y) {
-  const size_t psi_row = (size_t)g.npg * (vw / 4);
-  const size_t eslot_f4 = (size_t)kL16ERows * kL16ZR;
-  const size_t hslot_f4 = (size_t)kL16HRows * kL16ZR + 8 * psi_row + 4;
-  const size_t warp_f4 = 3 * eslot_f4 + 2 * hslot_f4 + (size_t)kLeanXR * 4 * kL16ZR;
-  return sizeof(float4) * warp_f4 * lean16_warps(tile_y);
-}
-
-template <typename T>
-inline bool lean16_configure(const Geom& g, int tile_y_req, int stages_req, int sms, int l2_bytes,
-                             SystolicCfg* cfg, std::string* why) {
-  constexpr int VW = VecTraits<T>::VW;
-  if (g.Zq > kL16ZR) { *why = "needs a z-column of at most 16 vectors"; return false; }
-  if (g.N / VW * 3 >= (1ll << 32)) { *why = "domain too large for 32-bit vector indices"; return false; }
-  int max_tile = 2 * kL16MaxWarps - 1;           // 2*NW - 1 owned columns fill NW warps exactly
-  while (max_tile >= 1 && lean16_smem_bytes(g, VW, max_tile) + 4096 > 227 * 1024) --max_tile;
-  if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
+template <typename T, int LPC>
+inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, int sms, int l2_bytes,
+                               SystolicCfg* cfg, std::string* why) {
+  using C = L16<T, LPC, l16_k<T>()>;
+  if (g.N / C::VW * 3 >= (1ll << 32)) { *why = "domain too large for 32-bit vector indices"; return false; }
+  const size_t warp_bytes = sizeof(float4) * C::warp_f4(g.npg);
+  int warps = C::MaxWarps;
+  while (warps >= 1 && warp_bytes * warps + 4096 > 227 * 1024) --warps;
+  if (warps < 1) { *why = "staging ring does not fit in shared memory"; return false; }
+  int max_tile = C::CW * warps - 1;              // CW*NW - 1 owned columns fill NW warps exactly
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
   if (max_tile > g.Y) max_tile = g.Y;
   const int ntiles = (g.Y + max_tile - 1) / max_tile;
   const int widest = (g.Y + ntiles - 1) / ntiles;
+  const int nw = (widest + C::CW) / C::CW;
   cfg->tile_y = widest;
   cfg->ntiles = ntiles;
-  cfg->cols = 16;                                // marks the half-warp variant for the launcher
-  cfg->threads = 32 * (lean16_warps(widest) + 1);
-  cfg->smem_bytes = (int)lean16_smem_bytes(g, VW, widest);
+  cfg->cols = 16;                                // marks the sub-warp variant for the launcher
+  cfg->threads = 32 * (nw + 1);
+  cfg->smem_bytes = (int)(warp_bytes * nw);
   cfg->max_lead = 10;
   cfg->pf_ahead = 6;
   cfg->svc_sleep_ns = 200;
   cfg->spin_ns_max = 160;
-  cfg->discard = (g.Zq % 8 == 0) ? 1 : 0;        // a column must be whole 128-byte lines
-  if (const char* e = getenv("B200FDTD_LEAN_DISCARD")) cfg->discard = cfg->discard && atoi(e);
+  // L2 discard of consumed lines: off by default here.  With these short columns (and half the
+  // bytes per cell in fp16) HBM is nowhere near its limit, and the CCTL instructions cost 4-5 %
+  // (256x256x128 fp16: 106.3 vs 102.4 Gcell/s; fp32 Z=64: 80.1 vs 76.3).  B200FDTD_LEAN_DISCARD=1
+  // turns it on where a column is whole 128-byte lines (halves the HBM traffic, lower power).
+  cfg->discard = 0;
+  if (const char* e = getenv("B200FDTD_LEAN_DISCARD")) cfg->discard = (g.Zq % 8 == 0) && atoi(e) != 0;
   if (const char* e = getenv("B200FDTD_SPIN_NS")) cfg->spin_ns_max = atoi(e);
   if (const char* e = getenv("B200FDTD_MAX_LEAD")) cfg->max_lead = atoi(e);
   if (const char* e = getenv("B200FDTD_PF_AHEAD")) cfg->pf_ahead = atoi(e);
@@ -540,7 +611,7 @@ inline bool lean16_configure(const Geom& g, int tile_y_req, int stages_req, int 
   cfg->need_zfix = 0;
   cfg->unroll = 1;
   int occ = 0;
-  const void* fn = (const void*)lean16_kernel<T>;
+  const void* fn = (const void*)lean16_kernel<T, LPC, l16_k<T>()>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -566,9 +637,18 @@ inline bool lean16_configure(const Geom& g, int tile_y_req, int stages_req, int 
 }
 
 template <typename T>
+inline bool lean16_configure(const Geom& g, int tile_y_req, int stages_req, int sms, int l2_bytes,
+                             SystolicCfg* cfg, std::string* why) {
+  if (g.Zq > kL16ZR) { *why = "needs a z-column of at most 16 vectors"; return false; }
+  return g.Zq <= 8 ? lean16_configure_i<T, 8>(g, tile_y_req, stages_req, sms, l2_bytes, cfg, why)
+                   : lean16_configure_i<T, 16>(g, tile_y_req, stages_req, sms, l2_bytes, cfg, why);
+}
+
+template <typename T>
 inline int lean16_launch(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
                          cudaStream_t st) {
-  const void* fn = (const void*)lean16_kernel<T>;
+  const void* fn = g.Zq <= 8 ? (const void*)lean16_kernel<T, 8, l16_k<T>()>
+                             : (const void*)lean16_kernel<T, 16, l16_k<T>()>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;

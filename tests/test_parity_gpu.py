@@ -172,7 +172,7 @@ def test_systolic_lean_rejects_other_geometries():
 
 @pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 128), (False, 64), (False, 30)])
 @pytest.mark.parametrize("axis", [0, 1, 2])
-@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (6, 3), (4, 40), (21, 2)])
+@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (6, 3), (4, 40), (21, 2), (31, 2)])
 def test_systolic_lean_halfwarp_tilings(tile_y, stages, axis, reduced, Z):
   """pjz's default engine geometry (fp16 storage, 96 z-cells) and its neighbours: every tiling,
   all source orientations, bit-exact against the C oracle (fp16 storage mode included)."""
@@ -201,6 +201,18 @@ def test_systolic_lean_halfwarp_ragged_domains(reduced, domain, pml, zb):
     np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean"), fdtd_c.fdtdz(**kw))
 
 
+@pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 60), (False, 64), (False, 32), (False, 14)])
+@pytest.mark.parametrize("tile_y,stages", [(0, 0), (5, 3), (9, 2), (17, 2), (40, 2), (63, 1)])
+def test_systolic_lean_subwarp_wide_tiles(tile_y, stages, reduced, Z):
+  """Many columns per warp (8 lanes per column and / or 2 columns per thread): tiles wider and
+  narrower than a warp's column group, tiles that end inside one."""
+  for axis in (1, 2):
+    kw = random_problem(domain=(9, 70, Z), axis=axis, pml=(5, 7), tt=21, seed=23 + axis,
+                        output_steps=(9, 21, 5), reduced=reduced)
+    out = run_gpu(kw, kernel="systolic_lean", tile_y=tile_y, stages=stages)
+    np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
+
+
 @pytest.mark.parametrize("reduced,Z", [(True, 96), (False, 64)])
 def test_systolic_lean_halfwarp_fused_projection(reduced, Z):
   kw = random_problem(domain=(9, 21, Z), axis=0, pml=(8, 8), tt=33, seed=91, output_steps=(8, 33, 4),
@@ -213,13 +225,13 @@ def test_systolic_lean_halfwarp_fused_projection(reduced, Z):
   np.testing.assert_array_equal(fdtdz_jax.fdtdz(**dev, output_projection=W).cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 128), (False, 64)])
+@pytest.mark.parametrize("reduced,Z", [(True, 96), (True, 128), (True, 64), (False, 64), (False, 32)])
 def test_systolic_lean_halfwarp_long_run_at_pjz_default_size(reduced, Z):
   """256x256 in x-y at pjz's default height, 300 steps through the full-size plan (L2 discard on
   when a column is whole 128-byte lines): bit-for-bit against the cp.async kernel, which shares
   neither the staging nor the discard logic; reduced precision within the stated bound of fp32."""
-  kw = random_problem(domain=(256, 256, Z), sub=(192, 192, Z - 32), offset=(32, 32, 16), axis=0,
-                      pml=(16, 16), tt=300, seed=6, output_steps=(120, 300, 89), absorb_pad=32,
+  kw = random_problem(domain=(256, 256, Z), sub=(192, 192, Z - 20), offset=(32, 32, 10), axis=0,
+                      pml=(16, 16) if Z > 32 else (8, 8), tt=300, seed=6, output_steps=(120, 300, 89), absorb_pad=32,
                       absorb_coeff=1e-4, reduced=reduced)
   a = run_gpu(kw, kernel="systolic_async")
   b = run_gpu(kw, kernel="systolic_lean")
@@ -266,9 +278,15 @@ def test_host_path_equals_device_path():
 
 
 def test_auto_plan_prefers_systolic_and_reports():
-  kw = random_problem(domain=(64, 64, 64), tt=20, seed=1)
+  kw = random_problem(domain=(64, 64, 48), tt=20, seed=1)
   info = fdtdz_jax.plan_info(**kw)
   assert info["kernel"] == "systolic_async" and info["ctas"] >= 1 and info["prefetch"] >= 1
+  # columns of <= 16 vectors whose lanes are (nearly) all busy: the sub-warp lean kernel
+  for domain, reduced, want in [((64, 64, 64), False, "systolic_lean"), ((64, 64, 128), True, "systolic_lean"),
+                                ((64, 64, 60), True, "systolic_lean"), ((64, 64, 96), True, "systolic_async"),
+                                ((64, 64, 32), False, "systolic_async"), ((64, 64, 128), False, "systolic_lean")]:
+    kw = random_problem(domain=domain, tt=20, seed=1, reduced=reduced)
+    assert fdtdz_jax.plan_info(**kw)["kernel"] == want, (domain, reduced)
 
 
 def test_no_outputs_and_zero_steps():
