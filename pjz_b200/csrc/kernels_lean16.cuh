@@ -56,7 +56,7 @@ struct Lean16Ctl {
   unsigned rcnt[12];
 };
 
-template <typename T, int LPC, int K>
+template <typename T, int LPC, int K, bool STATS = false>
 __global__ void __launch_bounds__(32 * (L16<T, LPC, K>::MaxWarps + 1), 1)
 lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sync) {
   using C = L16<T, LPC, K>;
@@ -239,6 +239,8 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   bool ok = true;
   unsigned kk = 0;                                 // cumulative iteration count (never reset)
   unsigned iters_done = 0;
+  long long st_cp = 0, st_avail = 0, st_next = 0, st_rc = 0, st_hc = 0;   // STATS: cycles waited
+  const long long st_begin = STATS ? clock64() : 0;
 
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
@@ -297,6 +299,14 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       const unsigned need = has_prev ? base_prev + (unsigned)min(it + 2, X) : 0u;
       const int lead = min(it, X) - 1 - cfg.max_lead;
       const unsigned need_next = (has_next && lead > 0) ? base_mine + (unsigned)lead : 0u;
+      if constexpr (STATS) {
+        const long long c0 = clock64();
+        const bool r0 = spin([&]() { return ld_vol_s(&ctl.avail) >= need; });
+        const long long c1 = clock64();
+        const bool r1 = r0 && spin([&]() { return ld_vol_s(&ctl.next) >= need_next; });
+        st_avail += c1 - c0; st_next += clock64() - c1;
+        return r1;
+      }
       return spin([&]() { return ld_vol_s(&ctl.avail) >= need && ld_vol_s(&ctl.next) >= need_next; });
     };
 
@@ -370,6 +380,11 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       const bool real = i >= 1;
       const int Pn = P + 1 == X ? 0 : P + 1;
       const unsigned vP = (unsigned)P * PVn;
+      if constexpr (STATS) {
+        const long long c0 = clock64();
+        cp_async_wait<0>();
+        st_cp += clock64() - c0;
+      }
       cp_async_wait<0>();                          // this lane's copies of iteration i have landed
       if (i < X) {
         ok = wait_deps(i + 1);
@@ -448,7 +463,9 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
         float4* const xs = xmine + (kk & (kLeanXR - 1)) * C::XF4;
         if (kk >= (unsigned)kLeanXR && w + 1 < NWt) {
           const unsigned need = kk + 1u - (unsigned)kLeanXR;
+          const long long c0 = STATS ? clock64() : 0;
           ok = spin([&]() { return ld_vol_s(&ctl.rcnt[w]) >= need; });
+          if constexpr (STATS) st_rc += clock64() - c0;
           if (!ok) break;
         }
         xs[0] = pack(hz[K - 1], T());
@@ -461,7 +478,9 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       if (real) {
         if (w > 0) {
           const unsigned need = kk + 1u;
+          const long long c0 = STATS ? clock64() : 0;
           ok = spin([&]() { return ld_vol_s(&ctl.hcnt[w - 1]) >= need; });
+          if constexpr (STATS) st_hc += clock64() - c0;
           if (!ok) break;
         }
         float hzm[VW], hxm[VW];                    // (Hz, Hx) of the column before this thread's first
@@ -564,12 +583,28 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   }
   cp_async_wait<0>();
   __syncwarp();
+  if constexpr (STATS) {
+    if (lane == 0 && (t == 0 || t == NT / 2)) {
+      const double tot = (double)(clock64() - st_begin);
+      printf("lean16stats j %d t %d w %d iters %u cyc/iter %.0f  cp %.3f avail %.3f next %.3f rcnt %.3f hcnt %.3f\n",
+             j, t, w, kk, tot / (kk ? kk : 1), st_cp / tot, st_avail / tot, st_next / tot,
+             st_rc / tot, st_hc / tot);
+    }
+  }
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
 }
 
 // Which instance serves a geometry: K = 2 columns per thread for fp32 (4 cells per vector), 1 for
 // fp16 (8 cells per vector); 8 lanes per column when the column has at most 8 vectors.
 template <typename T> constexpr int l16_k() { return sizeof(T) == 4 ? 2 : 1; }
+
+// B200FDTD_LEAN_STATS=1: the per-warp wait accounting build (prints at the end of the launch).
+template <typename T, int LPC>
+inline const void* lean16_fn() {
+  if (getenv("B200FDTD_LEAN_STATS") != nullptr)
+    return (const void*)lean16_kernel<T, LPC, l16_k<T>(), true>;
+  return (const void*)lean16_kernel<T, LPC, l16_k<T>(), false>;
+}
 
 template <typename T, int LPC>
 inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, int sms, int l2_bytes,
@@ -611,7 +646,7 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   cfg->need_zfix = 0;
   cfg->unroll = 1;
   int occ = 0;
-  const void* fn = (const void*)lean16_kernel<T, LPC, l16_k<T>()>;
+  const void* fn = lean16_fn<T, LPC>();
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -647,8 +682,7 @@ inline bool lean16_configure(const Geom& g, int tile_y_req, int stages_req, int 
 template <typename T>
 inline int lean16_launch(const Geom& g, const Ptrs<T>& p, const SystolicCfg& cfg, unsigned* sync,
                          cudaStream_t st) {
-  const void* fn = g.Zq <= 8 ? (const void*)lean16_kernel<T, 8, l16_k<T>()>
-                             : (const void*)lean16_kernel<T, 16, l16_k<T>()>;
+  const void* fn = g.Zq <= 8 ? lean16_fn<T, 8>() : lean16_fn<T, 16>();
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;
