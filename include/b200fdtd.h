@@ -187,11 +187,25 @@ int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, cons
  * grid_start / grid_end (zz, 2) [column 0: Ex/Ey cells, column 1: Ez cells], out (3, xx, yy, zz):
  * all device float32; workspace: b200fdtd_render_workspace_bytes(ll, xx, yy, zz) device bytes
  * (256-byte aligned).
- * Forward only (the reference differentiates it with jax.grad).  Asynchronous on `stream`. */
+ * Asynchronous on `stream`. */
 size_t b200fdtd_render_workspace_bytes(int ll, int xx, int yy, int zz);
 int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
                     const void* layer_pos, const void* grid_start, const void* grid_end,
                     int use_simple_averaging, void* workspace, void* out, void* stream);
+
+/* Vector-Jacobian product of b200fdtd_render (the reference differentiates pjz.render with
+ * jax.grad, /root/reference/tests/test_layers.py:179-188).  grad_out (3, xx, yy, zz) float32 =
+ * d loss / d epsilon; results: grad_layers (ll, 2m*xx, 2m*yy) float32 = d loss / d layers, and
+ * grad_overlap (2, 2, ll, zz) float64 = d loss / d [u | u*z][column][layer][z], the gradient with
+ * respect to the layer/cell overlap table of /root/reference/src/pjz/_epsilon.py:47-66 from which
+ * the caller forms d loss / d layer_pos (pjz_b200/_epsilon.py does it with four tensor ops).
+ * workspace: b200fdtd_render_backward_workspace_bytes(...) device bytes, 256-byte aligned.
+ * All pointers are device pointers; asynchronous on `stream`. */
+size_t b200fdtd_render_backward_workspace_bytes(int ll, int xx, int yy, int zz);
+int b200fdtd_render_backward(int ll, int xx, int yy, int zz, int m, const void* layers,
+                             const void* layer_pos, const void* grid_start, const void* grid_end,
+                             int use_simple_averaging, const void* grad_out, void* workspace,
+                             void* grad_layers, void* grad_overlap, void* stream);
 
 
 /* ---- Stepping sessions ---------------------------------------------------------------------------

@@ -737,6 +737,48 @@ int b200fdtd_render(int ll, int xx, int yy, int zz, int m, const void* layers,
   return B200FDTD_OK;
 }
 
+size_t b200fdtd_render_backward_workspace_bytes(int ll, int xx, int yy, int zz) {
+  if (ll < 1 || xx < 1 || yy < 1 || zz < 1) return 0;
+  return align_up(b200fdtd_render_workspace_bytes(ll, xx, yy, zz), 256) +
+         (size_t)3 * ll * xx * yy * 4 * sizeof(double);
+}
+
+int b200fdtd_render_backward(int ll, int xx, int yy, int zz, int m, const void* layers,
+                             const void* layer_pos, const void* grid_start, const void* grid_end,
+                             int use_simple_averaging, const void* grad_out, void* workspace,
+                             void* grad_layers, void* grad_overlap, void* stream) {
+  if (ll < 1 || xx < 1 || yy < 1 || zz < 1 || m < 1)
+    return fail(B200FDTD_EINVAL, "render_backward: ll, xx, yy, zz, m must be positive");
+  if (!layers || !grid_start || !grid_end || !grad_out || !workspace || !grad_layers ||
+      !grad_overlap || (ll > 1 && !layer_pos))
+    return fail(B200FDTD_EINVAL, "render_backward: NULL argument");
+  if ((size_t)2 * zz * sizeof(double) > 48 * 1024)
+    return fail(B200FDTD_EUNSUPPORTED, "render_backward: zz too large for the block reduction");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b > 148 * 32 ? 148 * 32 : b); };
+  char* ws = static_cast<char*>(workspace);
+  float4* stats = reinterpret_cast<float4*>(ws);
+  double* tab = reinterpret_cast<double*>(ws + render_stats_bytes(ll, xx, yy));
+  double* dstats = reinterpret_cast<double*>(
+      ws + align_up(b200fdtd_render_workspace_bytes(ll, xx, yy, zz), 256));
+  // forward quantities again (cheap next to keeping them alive across the engine runs)
+  tile_stats_kernel<<<blocks((size_t)3 * ll * xx * yy), 256, 0, st>>>(
+      ll, xx, yy, m, static_cast<const float*>(layers), stats);
+  layer_overlap_kernel<<<blocks((size_t)2 * ll * zz), 256, 0, st>>>(
+      ll, zz, static_cast<const float*>(layer_pos), static_cast<const float*>(grid_start),
+      static_cast<const float*>(grid_end), tab);
+  CUDA_TRY(cudaMemsetAsync(grad_overlap, 0, (size_t)4 * ll * zz * sizeof(double), st));
+  unsigned bx = (unsigned)(((size_t)xx * yy + 255) / 256);
+  if (bx > 148 * 4) bx = 148 * 4;
+  render_combine_bwd_kernel<<<dim3(bx, 3 * ll), 256, 2 * zz * sizeof(double), st>>>(
+      ll, xx, yy, zz, stats, tab, use_simple_averaging, static_cast<const float*>(grad_out), dstats,
+      static_cast<double*>(grad_overlap));
+  tile_stats_bwd_kernel<<<blocks((size_t)ll * 4 * m * m * xx * yy), 256, 0, st>>>(
+      ll, xx, yy, m, static_cast<const float*>(layers), dstats, static_cast<float*>(grad_layers));
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
 
 // ---- stepping sessions (host-driven time loops: domain decomposition with halo exchange) ------
 

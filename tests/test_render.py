@@ -139,3 +139,127 @@ def test_epsilon_feeds_the_engine_without_leaving_the_gpu(built):
   a = fdtdz_jax.fdtdz(**kw).cpu().numpy()
   kw["epsilon"] = eps.cpu().numpy()
   np.testing.assert_array_equal(a, fdtdz_jax.fdtdz(**kw))
+
+
+# ---- backward pass (the reference differentiates pjz.render with jax.grad,
+# /root/reference/tests/test_layers.py:179-188) -------------------------------------------------------
+
+def _random_stack(ll, xx, yy, zz, m, seed):
+  rng = np.random.default_rng(seed)
+  layers = rng.uniform(1.0, 12.25, (ll, 2 * m * xx, 2 * m * yy))
+  pos = np.sort(rng.uniform(0.5, zz - 1.5, ll - 1))
+  gs = np.arange(zz)[:, None] * 1.1 + np.array([[-0.5, 0]])          # stretched grid
+  ge = np.arange(zz)[:, None] * 1.1 + np.array([[0.6, 1.1]])
+  wts = rng.standard_normal((3, xx, yy, zz))                         # d loss / d epsilon
+  return layers, pos, gs, ge, wts
+
+
+@pytest.mark.parametrize("simple", [False, True])
+def test_torch_oracle_equals_numpy_oracle_and_its_gradient_matches_differences(simple):
+  """The differentiable float64 restatement (oracle/render_torch.py) agrees with the NumPy oracle
+  -- which the golden values above pin -- and its autograd gradient with central differences of
+  the NumPy oracle, for layers and layer_pos."""
+  import torch
+  from oracle import render_torch
+  ll, xx, yy, zz, m = 3, 3, 2, 4, 2
+  layers, pos, gs, ge, wts = _random_stack(ll, xx, yy, zz, m, 11)
+  want = render_numpy.render(layers, pos, gs, ge, m, simple)
+  lt = torch.tensor(layers, requires_grad=True)
+  pt = torch.tensor(pos, requires_grad=True)
+  got = render_torch.render(lt, pt, torch.tensor(gs), torch.tensor(ge), m, simple)
+  np.testing.assert_allclose(got.detach().numpy(), want, rtol=1e-12)
+  (got * torch.tensor(wts)).sum().backward()
+  loss = lambda L, P: float((render_numpy.render(L, P, gs, ge, m, simple) * wts).sum())
+  h = 1e-6
+  rng = np.random.default_rng(0)
+  for idx in [tuple(rng.integers(0, s) for s in layers.shape) for _ in range(25)] + \
+             [(0, 0, 0), (1, 0, 3), (2, 5, 0), (0, 2 * m * xx - 1, 2 * m * yy - 1)]:
+    d = np.zeros_like(layers); d[idx] = h
+    fd = (loss(layers + d, pos) - loss(layers - d, pos)) / (2 * h)
+    assert lt.grad[idx].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), idx
+  for k in range(ll - 1):
+    d = np.zeros_like(pos); d[k] = h
+    fd = (loss(layers, pos + d) - loss(layers, pos - d)) / (2 * h)
+    assert pt.grad[k].item() == pytest.approx(fd, rel=2e-5, abs=1e-8), k
+
+
+def test_torch_oracle_is_differentiable_like_the_reference():
+  # /root/reference/tests/test_layers.py:179-188 on the oracle
+  import torch
+  from oracle import render_torch
+  xx, yy, zz = 2, 2, 2
+  lay = torch.ones((2, 2 * xx, 2 * yy), dtype=torch.float64, requires_grad=True)
+  pos = torch.tensor([1.0], dtype=torch.float64, requires_grad=True)
+  gs, ge = Z(zz)
+  render_torch.render(lay, pos, torch.tensor(gs), torch.tensor(ge), 1).sum().backward()
+  assert lay.grad.shape == (2, 2 * xx, 2 * yy) and pos.grad.shape == (1,)
+
+
+@pytest.mark.gpu
+def test_cuda_renderer_is_differentiable_like_the_reference(built):
+  # /root/reference/tests/test_layers.py:179-188 on the CUDA renderer
+  import torch
+  from pjz_b200._epsilon import render
+  xx, yy, zz = 2, 2, 2
+  lay = torch.ones((2, 2 * xx, 2 * yy), device="cuda", requires_grad=True)
+  pos = torch.tensor([1.0], device="cuda", requires_grad=True)
+  gs, ge = Z(zz)
+  render(lay, pos, gs, ge, 1).sum().backward()
+  assert lay.grad.shape == (2, 2 * xx, 2 * yy) and pos.grad.shape == (1,)
+  assert torch.isfinite(lay.grad).all() and torch.isfinite(pos.grad).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ll,xx,yy,zz,m,simple", [(1, 5, 4, 3, 1, False), (2, 2, 2, 2, 1, False),
+                                                 (3, 9, 7, 12, 2, False), (4, 16, 12, 20, 4, False),
+                                                 (3, 6, 5, 8, 3, True), (5, 33, 17, 96, 2, False)])
+def test_cuda_renderer_backward_matches_the_torch_oracle(ll, xx, yy, zz, m, simple, built):
+  """b200fdtd_render_backward (d/d layers, d/d layer_pos) against autograd through the float64
+  torch restatement; tolerance 2e-5 of the gradient's largest entry (the forward's tile
+  statistics are held in float32)."""
+  import torch
+  from oracle import render_torch
+  from pjz_b200._epsilon import render
+  layers, pos, gs, ge, wts = _random_stack(ll, xx, yy, zz, m, ll * 100 + m)
+  lt = torch.tensor(layers, requires_grad=True)
+  pt = torch.tensor(pos, requires_grad=True)
+  (render_torch.render(lt, pt, torch.tensor(gs), torch.tensor(ge), m, simple) * torch.tensor(wts)).sum().backward()
+  lc = torch.tensor(layers, dtype=torch.float32, device="cuda", requires_grad=True)
+  pc = torch.tensor(pos, dtype=torch.float32, device="cuda", requires_grad=True)
+  out = render(lc, pc, gs, ge, m, simple)
+  (out * torch.tensor(wts, dtype=torch.float32, device="cuda")).sum().backward()
+  gl, wl = lc.grad.cpu().double(), lt.grad
+  assert gl.shape == wl.shape
+  assert float((gl - wl).abs().max()) <= 2e-5 * float(wl.abs().max())
+  if ll > 1:
+    gp, wp = pc.grad.cpu().double(), pt.grad
+    assert float((gp - wp).abs().max()) <= 2e-5 * float(wp.abs().max()) + 1e-7
+
+
+@pytest.mark.gpu
+def test_gradient_flows_from_the_engine_loss_to_the_layers(built):
+  """layers -> epsilon (CUDA renderer) -> scatter (CUDA engine, fused adjoint backward) -> loss:
+  one backward() reaches the layer image and the interface positions on the GPU."""
+  import torch
+  from pjz_b200 import SimParams, mode, scatter
+  from pjz_b200._epsilon import epsilon
+  omega = np.array([2 * np.pi / 37])
+  xx, yy, zz = 40, 30, 20
+  lay = np.full((3, 2 * xx, 2 * yy), 1.0, np.float32)
+  lay[1, :, 2 * 9:2 * 21] = 12.25                        # Si strip in the middle layer
+  lt = torch.tensor(lay, device="cuda", requires_grad=True)
+  pos = torch.tensor([7.5, 11.5], device="cuda", requires_grad=True)
+  eps = epsilon(lt, pos, 1, zz)
+  assert eps.requires_grad and tuple(eps.shape) == (3, xx, yy, zz)
+  e_np = eps.detach().cpu().numpy()
+  b0, x0, _, _ = mode(e_np[:, 6:7], omega, 1)
+  b1, x1, _, _ = mode(e_np[:, 33:34], omega, 1)
+  p = SimParams(omega_range=(omega[0], omega[0]), tt=400, dt=0.5, absorption_padding=10,
+                absorption_coeff=4e-4, pml_widths=(6, 6), use_reduced_precision=False, domain_zz=32)
+  sv = scatter(eps, omega, [x0[..., 0], x1[..., 0]], [b0[:, 0], b1[:, 0]], [6, 33], [True, False], p,
+               fuse_projection=True)
+  loss = sum((s.abs() ** 2).sum() for row in sv for s in row)
+  loss.backward()
+  assert lt.grad is not None and lt.grad.shape == lt.shape and torch.isfinite(lt.grad).all()
+  assert float(lt.grad.abs().max()) > 0
+  assert pos.grad is not None and pos.grad.shape == (2,) and torch.isfinite(pos.grad).all()
