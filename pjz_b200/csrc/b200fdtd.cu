@@ -795,8 +795,9 @@ struct b200fdtd_session {
   dim3 grid;
 };
 
-// Sessions use the warp-per-column-pair systolic kernel when the plan selects it (fp32, 32
-// z-vectors) and the per-step kernels otherwise.
+// Sessions use the lean systolic kernels when the plan selects them (fp32 with 32 z-vectors, or
+// the sub-warp variant for short columns in either storage type) and the per-step kernels
+// otherwise.
 static int session_plan(const b200fdtd_desc* desc, const Geom& g, Plan* plan, bool* systolic) {
   *systolic = false;
   plan->kernel = B200FDTD_KERNEL_TWOPASS;
@@ -808,7 +809,7 @@ static int session_plan(const b200fdtd_desc* desc, const Geom& g, Plan* plan, bo
     if (desc->kernel == B200FDTD_KERNEL_AUTO) return B200FDTD_OK;
     return rc;
   }
-  if (p.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN && p.sys.cols != 16) {
+  if (p.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
     *plan = p;
     *systolic = true;
   } else if (desc->kernel != B200FDTD_KERNEL_AUTO) {
@@ -904,8 +905,13 @@ int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stre
   g.tt = n0 + nsteps;
   CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
   unsigned* const sync = reinterpret_cast<unsigned*>(s->ws + s->w.sync);
-  const int rc = s->plan.sys.cols == 1 ? lean1_launch(g, s->pf, s->plan.sys, sync, st)
-                                       : lean_launch(g, s->pf, s->plan.sys, sync, st);
+  int rc;
+  if (s->plan.sys.cols == 16)                      // sub-warp variant: fp16 or fp32 storage
+    rc = s->reduced ? lean16_launch<__half>(g, s->ph, s->plan.sys, sync, st)
+                    : lean16_launch<float>(g, s->pf, s->plan.sys, sync, st);
+  else
+    rc = s->plan.sys.cols == 1 ? lean1_launch(g, s->pf, s->plan.sys, sync, st)
+                               : lean_launch(g, s->pf, s->plan.sys, sync, st);
   if (rc != 0)
     return fail(B200FDTD_ECUDA, "systolic launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return B200FDTD_OK;

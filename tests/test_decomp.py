@@ -242,7 +242,10 @@ def test_y_session_driver_equals_one_call_engine(built):
   from tests.problems import random_problem
   cases = [((10, 40, 128), (16, 16), 0, 6, False), ((9, 36, 128), (4, 6), 1, 4, False),
            ((8, 30, 126), (0, 0), 2, 7, False), ((12, 20, 40), (5, 6), 0, 3, False),
-           ((10, 24, 32), (4, 4), 1, 2, True)]
+           ((10, 24, 32), (4, 4), 1, 2, True),
+           # short columns: the sub-warp lean kernel advances the slab (fp16 and fp32 storage)
+           ((10, 40, 128), (16, 16), 0, 6, True), ((9, 36, 64), (4, 6), 1, 4, False),
+           ((8, 30, 60), (0, 0), 2, 7, True), ((11, 50, 100), (12, 9), 1, 5, True)]
   for domain, pml, axis, ghost, reduced in cases:
     kw = random_problem(domain=domain, axis=axis, pml=pml, tt=27, seed=80 + axis,
                         output_steps=(9, 27, 5), reduced=reduced)
@@ -252,6 +255,9 @@ def test_y_session_driver_equals_one_call_engine(built):
     got = fdtdz_decomposed_y(**kw, ghost=ghost).cpu().numpy()
     np.testing.assert_array_equal(got, want)
   run = YSlabRun(random_problem(domain=(10, 40, 128), pml=(16, 16), tt=8, seed=1), ghost=4)
+  assert run.slab.kernel == "systolic_lean" and run.slab.pingpong
+  run.close()
+  run = YSlabRun(random_problem(domain=(10, 40, 128), pml=(16, 16), tt=8, seed=1, reduced=True), ghost=4)
   assert run.slab.kernel == "systolic_lean" and run.slab.pingpong
   run.close()
 
