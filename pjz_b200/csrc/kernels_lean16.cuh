@@ -43,7 +43,7 @@ struct L16 {
   static constexpr int ERows = 3 * CW + 2;       // Ex[0..CW], Ez[0..CW], Ey[0..CW-1]
   static constexpr int HRows = 6 * CW;           // Hx, Hy, Hz, Bx, By, Bz [0..CW-1]
   static constexpr int XF4 = G * 2 * LPC;        // float4 per boundary-slot ring entry (= 64)
-  static constexpr int MaxWarps = K == 2 ? 8 : 11;   // compute warps per CTA (+1 service warp)
+  static constexpr int MaxWarps = K == 2 ? 8 : 11;   // compute warps per CTA (+1 service warp): 12 warps = 168 registers; a 13th rounds up to 16 warps = 128
   static size_t eslot_f4() { return (size_t)ERows * LPC; }
   static size_t hslot_f4(int npg) { return (size_t)HRows * LPC + 4 * CW * (size_t)npg * PV + 2 * CW; }
   static size_t warp_f4(int npg) { return 3 * eslot_f4() + 2 * hslot_f4(npg) + (size_t)kLeanXR * XF4; }
