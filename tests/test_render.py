@@ -263,3 +263,42 @@ def test_gradient_flows_from_the_engine_loss_to_the_layers(built):
   assert lt.grad is not None and lt.grad.shape == lt.shape and torch.isfinite(lt.grad).all()
   assert float(lt.grad.abs().max()) > 0
   assert pos.grad is not None and pos.grad.shape == (2,) and torch.isfinite(pos.grad).all()
+
+
+def test_overlap_table_host_logic_matches_the_reference_formulas():
+  """pjz_b200._epsilon._overlap_table (the host-side link between b200fdtd_render_backward's
+  overlap-table gradient and d/d layer_pos) against /root/reference/src/pjz/_epsilon.py:55-66
+  restated with NumPy, and its derivative against differences."""
+  import torch
+  from pjz_b200._epsilon import _overlap_table
+  rng = np.random.default_rng(4)
+  zz, ll = 9, 4
+  pos = np.sort(rng.uniform(0.3, zz - 1.2, ll - 1))
+  gs = np.arange(zz)[:, None] * 1.05 + np.array([[-0.5, 0]])
+  ge = np.arange(zz)[:, None] * 1.05 + np.array([[0.55, 1.05]])
+
+  def table(p):
+    us, uzs = [], []
+    for col in (0, 1):
+      s, e = gs[:, col], ge[:, col]
+      p0, p1 = [np.clip(x[:, None], s, e) for x in (np.concatenate([[-np.inf], p]),
+                                                    np.concatenate([p, [np.inf]]))]
+      u = (p1 - p0) / (e - s)
+      us.append(u); uzs.append(u * ((p0 + p1) / 2 - (s + e) / 2))
+    return np.stack(us), np.stack(uzs)
+
+  pt = torch.tensor(pos, requires_grad=True)
+  u, uz = _overlap_table(pt, torch.tensor(gs, dtype=torch.float32), torch.tensor(ge, dtype=torch.float32))
+  wu, wuz = table(pos)
+  assert tuple(u.shape) == (2, ll, zz)
+  np.testing.assert_allclose(u.detach().numpy(), wu, atol=1e-6)
+  np.testing.assert_allclose(uz.detach().numpy(), wuz, atol=1e-6)
+  np.testing.assert_allclose(u.detach().numpy().sum(1), 1.0, atol=1e-12)     # layers tile every cell
+  cu, cuz = rng.standard_normal(wu.shape), rng.standard_normal(wuz.shape)
+  ((u * torch.tensor(cu)).sum() + (uz * torch.tensor(cuz)).sum()).backward()
+  h = 1e-6
+  for k in range(ll - 1):
+    d = np.zeros_like(pos); d[k] = h
+    (a0, b0), (a1, b1) = table(pos - d), table(pos + d)
+    fd = (((a1 - a0) * cu).sum() + ((b1 - b0) * cuz).sum()) / (2 * h)
+    assert pt.grad[k].item() == pytest.approx(fd, rel=1e-4, abs=1e-6)
