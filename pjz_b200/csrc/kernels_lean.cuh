@@ -325,10 +325,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     // E-only column of the last warp) and the prologue plane are copied all the same -- the
     // addresses are valid, the values unused -- because predicating two thirds of these copies
     // on warp-uniform flags cost more instructions than the copies themselves.
-    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first, bool /*ecoef*/) {
+    auto issue_e = [&](int PL, int PLn, float4* se, float4* se_first) {
       const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
       float4* const d = se + q;
-      float4* const h = sh + q;
       cp_async16(d + 0 * ZQ, rEx + (vN + tvA));
       cp_async16(d + 3 * ZQ, rEz + (vN + tvA));
       cp_async16(d + 6 * ZQ, rEy + (vN + tvA));
@@ -337,6 +336,25 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       cp_async16(d + 7 * ZQ, rEy + (vN + tvB));
       cp_async16(d + 2 * ZQ, rEx + (vN + tvC));
       cp_async16(d + 5 * ZQ, rEz + (vN + tvC));
+      if (se_first) {                                // very first plane of the sweep: E[PL] too
+        float4* const f = se_first + q;
+        cp_async16(f + 0 * ZQ, rEx + (vP + tvA));
+        cp_async16(f + 3 * ZQ, rEz + (vP + tvA));
+        cp_async16(f + 6 * ZQ, rEy + (vP + tvA));
+        cp_async16(f + 1 * ZQ, rEx + (vP + tvB));
+        cp_async16(f + 4 * ZQ, rEz + (vP + tvB));
+        cp_async16(f + 7 * ZQ, rEy + (vP + tvB));
+        cp_async16(f + 2 * ZQ, rEx + (vP + tvC));
+        cp_async16(f + 5 * ZQ, rEz + (vP + tvC));
+      }
+    };
+    // The H/B/psi/absorber half of the copies is issued after the H half-step, not right behind
+    // issue_e: the slot it fills (hnext) is idle for the whole iteration, and two shorter bursts
+    // queue up less in the load/store pipe than one of ~30 (ncu: the first instructions that reuse
+    // a copy's address registers sat on the long scoreboard; measured +1.5 % on cfg2).
+    auto issue_h = [&](int PL, float4* sh) {
+      const unsigned vP = (unsigned)PL * PVn;
+      float4* const h = sh + q;
       cp_async16(h + 0 * ZQ, rHx + (vP + tvA));
       cp_async16(h + 2 * ZQ, rHy + (vP + tvA));
       cp_async16(h + 4 * ZQ, rHz + (vP + tvA));
@@ -367,17 +385,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         cp_async16(ps + 5 * psi_row, ePx + (pp + pvB));
         cp_async16(ps + 7 * psi_row, ePy + (pp + pvB));
       }
-      if (se_first) {                                // very first plane of the sweep: E[PL] too
-        float4* const f = se_first + q;
-        cp_async16(f + 0 * ZQ, rEx + (vP + tvA));
-        cp_async16(f + 3 * ZQ, rEz + (vP + tvA));
-        cp_async16(f + 6 * ZQ, rEy + (vP + tvA));
-        cp_async16(f + 1 * ZQ, rEx + (vP + tvB));
-        cp_async16(f + 4 * ZQ, rEz + (vP + tvB));
-        cp_async16(f + 7 * ZQ, rEy + (vP + tvB));
-        cp_async16(f + 2 * ZQ, rEx + (vP + tvC));
-        cp_async16(f + 5 * ZQ, rEz + (vP + tvC));
-      }
+    };
+    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first, bool /*ecoef*/) {
+      issue_e(PL, PLn, se, se_first);
+      issue_h(PL, sh);
     };
 
     // TMA flavour of issue(): executed by lane 0 only.  Columns A, B (and C) of a pair are
@@ -527,9 +538,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         if (i < X) {
           ok = wait_deps(i + 1);
           if (!ok) break;
-          issue(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, hnext, nullptr, true);
+          issue_e(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, nullptr);
         }
-        cp_async_commit();
         __syncwarp();                              // the absorber rows were copied by lanes 0, 1
       }
       if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
@@ -600,6 +610,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
           h_cell(exB[v], eyB[v], ezB[v], exz, eyz, ezC[v], exC[v], eyxB[v], ezxB[v], ah[v], bh[v],
                  ikh[v], dt, psxB[v], psyB[v], hxB[v], hyB[v], hzB[v]);
         }
+      }
+      if constexpr (!TMA) {                        // second half of the copies for iteration i + 1
+        if (i < X) issue_h(Pn, hnext);
+        cp_async_commit();
       }
       // boundary H for the next warp: wait until it has consumed the slot's previous content
       {

@@ -312,15 +312,34 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
 
     // Async copies of one iteration (plane PL): E[PL+1] -> E slot se; H, B, psi, absorber row of
     // PL -> H/B slot sh.  Straight-line: halo / E-only / clamped columns are copied all the same.
-    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first) {
+    auto issue_e = [&](int PL, int PLn, float4* se, float4* se_first) {
       const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         float4* const d = se + (K * h + k) * LPC + q;
-        float4* const hh = sh + (K * h + k) * LPC + q;
         cp_async16(d, rEx + (vN + tv[k]));
         cp_async16(d + (CW + 1) * LPC, rEz + (vN + tv[k]));
         cp_async16(d + 2 * (CW + 1) * LPC, rEy + (vN + tv[k]));
+      }
+      if (G == 2 || h < 2) cp_async16(se + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vN + tvC));
+      if (se_first) {                                // very first plane of the sweep: E[PL] too
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float4* const f = se_first + (K * h + k) * LPC + q;
+          cp_async16(f, rEx + (vP + tv[k]));
+          cp_async16(f + (CW + 1) * LPC, rEz + (vP + tv[k]));
+          cp_async16(f + 2 * (CW + 1) * LPC, rEy + (vP + tv[k]));
+        }
+        if (G == 2 || h < 2) cp_async16(se_first + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vP + tvC));
+      }
+    };
+    // H, B, psi, absorber / z-source rows: issued after the H half-step (the slot they fill is
+    // idle for the whole iteration; two shorter bursts instead of one, see kernels_lean.cuh)
+    auto issue_h = [&](int PL, float4* sh) {
+      const unsigned vP = (unsigned)PL * PVn;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float4* const hh = sh + (K * h + k) * LPC + q;
         cp_async16(hh + 0 * CW * LPC, rHx + (vP + tv[k]));
         cp_async16(hh + 1 * CW * LPC, rHy + (vP + tv[k]));
         cp_async16(hh + 2 * CW * LPC, rHz + (vP + tv[k]));
@@ -328,7 +347,6 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
         cp_async16(hh + 4 * CW * LPC, By + (vP + tv[k]));
         cp_async16(hh + 5 * CW * LPC, Bz + (vP + tv[k]));
       }
-      if (G == 2 || h < 2) cp_async16(se + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vN + tvC));
       float4* const tail = sh + C::HRows * LPC + 4 * CW * psi_row;
       if (q < K) cp_async16(tail + K * h + q, A4 + ((unsigned)PL * (unsigned)Y + ya));
       if (zsrc && q >= K && q < 2 * K)
@@ -347,16 +365,10 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
           }
         }
       }
-      if (se_first) {                                // very first plane of the sweep: E[PL] too
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float4* const f = se_first + (K * h + k) * LPC + q;
-          cp_async16(f, rEx + (vP + tv[k]));
-          cp_async16(f + (CW + 1) * LPC, rEz + (vP + tv[k]));
-          cp_async16(f + 2 * (CW + 1) * LPC, rEy + (vP + tv[k]));
-        }
-        if (G == 2 || h < 2) cp_async16(se_first + (h ? 2 * CW + 1 : CW) * LPC + q, rEc + (vP + tvC));
-      }
+    };
+    auto issue = [&](int PL, int PLn, float4* se, float4* sh, float4* se_first) {
+      issue_e(PL, PLn, se, se_first);
+      issue_h(PL, sh);
     };
 
     int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
@@ -389,9 +401,8 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       if (i < X) {
         ok = wait_deps(i + 1);
         if (!ok) break;
-        issue(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, hnext, nullptr);
+        issue_e(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, nullptr);
       }
-      cp_async_commit();
       __syncwarp();                                // ... and so have those of the other lanes
       if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
       // Dead lines (see kernels_lean.cuh): Ey and H of every column and (Ex, Ez) of every column
@@ -458,6 +469,8 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
           }
         }
       }
+      if (i < X) issue_h(Pn, hnext);               // second half of the copies for iteration i + 1
+      cp_async_commit();
       // boundary H for the next column: the last sub-group waits until warp w+1 has consumed the slot
       {
         float4* const xs = xmine + (kk & (kLeanXR - 1)) * C::XF4;
