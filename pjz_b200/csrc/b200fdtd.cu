@@ -200,11 +200,12 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   }
   // Columns of at most 16 vectors (everything fdtd-z itself accepts): the sub-warp lean kernel
   // where most of its lanes carry a vector.  Measured on 256x256 in x-y (Gcell/s, lean16 vs the
-  // cp.async kernel): fp16 Z=128 106 vs 85, fp16 Z=64 (8 lanes per column) 98 vs 80, fp32 Z=64
-  // 80 vs 73; with 12 of 16 lanes busy (fp16 Z=96) it only ties (78 vs 82), and fp32 columns of
-  // <= 8 vectors are slower (63 vs 70), so those stay on the cp.async kernel.
+  // cp.async kernel, profiles/r01_lean16_pjz_geometries_final.txt): fp16 Z=128 119 vs 86, fp16
+  // Z=96 (pjz's default; 12 of 16 lanes busy) 85 vs 82, fp16 Z=64 (8 lanes per column) 109 vs 77,
+  // fp32 Z=64 83 vs 73; fp32 columns of <= 12 vectors are slower (Z=48 62 vs 67, Z=32 67 vs 70)
+  // and stay on the cp.async kernel.
   if (d->kernel == B200FDTD_KERNEL_AUTO && g.Zq <= kL16ZR) {
-    const bool wide = sizeof(T) == 2 ? ((g.Zq >= 13) || (g.Zq >= 7 && g.Zq <= 8)) : g.Zq >= 15;
+    const bool wide = sizeof(T) == 2 ? ((g.Zq >= 12) || (g.Zq >= 7 && g.Zq <= 8)) : g.Zq >= 15;
     if (wide && lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why)) {
       plan->kernel = B200FDTD_KERNEL_SYSTOLIC_LEAN;
       plan->depth = 1;

@@ -283,7 +283,8 @@ def test_auto_plan_prefers_systolic_and_reports():
   assert info["kernel"] == "systolic_async" and info["ctas"] >= 1 and info["prefetch"] >= 1
   # columns of <= 16 vectors whose lanes are (nearly) all busy: the sub-warp lean kernel
   for domain, reduced, want in [((64, 64, 64), False, "systolic_lean"), ((64, 64, 128), True, "systolic_lean"),
-                                ((64, 64, 60), True, "systolic_lean"), ((64, 64, 96), True, "systolic_async"),
+                                ((64, 64, 60), True, "systolic_lean"), ((64, 64, 96), True, "systolic_lean"),
+                                ((64, 64, 80), True, "systolic_async"),
                                 ((64, 64, 32), False, "systolic_async"), ((64, 64, 128), False, "systolic_lean")]:
     kw = random_problem(domain=domain, tt=20, seed=1, reduced=reduced)
     assert fdtdz_jax.plan_info(**kw)["kernel"] == want, (domain, reduced)
