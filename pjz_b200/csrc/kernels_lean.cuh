@@ -12,7 +12,10 @@
 //    ahead and is the only reader of what it copied: cp.async.wait_group is all the
 //    synchronisation the ring needs.  B[P], psiE[P] and the absorber row travel the same way
 //    (plain loads issued at the top of the iteration were measured to stall the first
-//    shared-memory read of the H half-step: they end up on the same scoreboard).
+//    shared-memory read of the H half-step: they end up on the same scoreboard).  The copies of
+//    one iteration go out in two bursts -- E[P+2] at the top, H/B/psi[P+1] after the H half-step
+//    -- and form one commit group: a single burst of ~30 LDGSTS queued up in the load/store pipe
+//    and held the address registers the next instructions wanted (long-scoreboard stalls).
 //  * The only data that crosses warps is the freshly formed (Hz, Hx) of the pair's second
 //    column -- the y-1 neighbour of the next warp's first column.  It goes through a 2-deep
 //    per-warp shared-memory slot guarded by two monotonic counters (produced / consumed):
