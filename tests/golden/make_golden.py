@@ -26,6 +26,14 @@ CASES = {
     "z_batch": dict(domain=(10, 9, 8), axis=0, pml=(0, 0), tt=20, seed=104, z_as_batch=True,
                     output_steps=(15, 20, 2)),
     "ragged_z": dict(domain=(7, 9, 13), axis=2, pml=(3, 5), tt=18, seed=105, output_steps=(9, 18, 3)),
+    # column heights that select the warp-per-column-pair kernel (32 fp32 vectors) and its
+    # sub-warp variants (16 and 8 vectors) under launch_params "auto" / "systolic_lean"
+    "tall_128": dict(domain=(6, 9, 128), sub=(3, 4, 120), axis=0, pml=(16, 16), tt=20, seed=106,
+                     output_steps=(13, 20, 6)),
+    "short_64": dict(domain=(6, 9, 64), sub=(3, 4, 60), axis=1, pml=(8, 8), tt=20, seed=107,
+                     output_steps=(13, 20, 6)),
+    "short_30": dict(domain=(5, 11, 30), sub=(3, 5, 26), axis=2, pml=(5, 7), tt=20, seed=108,
+                     output_steps=(13, 20, 6)),
 }
 
 

@@ -44,11 +44,22 @@ def _built(built):
   assert os.path.exists(fdtdz_jax.LIB_PATH)
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", KERNELS + ["auto"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_golden_vectors(name, kernel):
   kw = random_problem(**CASES[name])
   out = run_gpu(kw, kernel=kernel)
+  assert out.shape == GOLDEN[name].shape
+  assert rel_l2(out, GOLDEN[name]) <= FP32_TOL
+  np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
+
+
+@pytest.mark.parametrize("name", ["tall_128", "short_64", "short_30"])
+def test_golden_vectors_lean_kernels(name):
+  """The committed golden vectors whose column height fits the warp-per-column-pair kernel
+  (32 fp32 vectors) and its sub-warp variants (16 and 8 vectors), through kernel="systolic_lean"."""
+  kw = random_problem(**CASES[name])
+  out = run_gpu(kw, kernel="systolic_lean")
   assert out.shape == GOLDEN[name].shape
   assert rel_l2(out, GOLDEN[name]) <= FP32_TOL
   np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
