@@ -43,7 +43,7 @@ def parse():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="bend", choices=["bend", "waveguide", "demux", "coupler"])
   ap.add_argument("--tt", type=int, default=0, help="override the number of FDTD steps")
-  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic", "systolic_async", "systolic_tma",
+  ap.add_argument("--kernel", default="auto", choices=["auto", "twopass", "systolic", "systolic_async",
                                                        "systolic_lean"])
   ap.add_argument("--tile-y", type=int, default=0)
   ap.add_argument("--stages", type=int, default=0)
@@ -332,8 +332,8 @@ def main():
   achieved = per_gpu * bpc                       # GB/s of ALGORITHMIC traffic
   traffic = ncu_traffic()
   if info["kernel"].startswith("systolic"):
-    kname = {"systolic_lean": "lean_kernel", "systolic_async": "systolic2_kernel",
-             "systolic_tma": "systolic3_kernel"}.get(info["kernel"], "systolic_kernel")
+    kname = {"systolic_lean": "lean_kernel",
+             "systolic_async": "systolic2_kernel"}.get(info["kernel"], "systolic_kernel")
     if info["kernel"] == "systolic_lean" and (args.reduced or dims[2] <= 64):
       kname = "lean16_kernel"                    # sub-warp variant: columns of <= 16 vectors
     dominant = kname + " (1 launch per engine call; duration = call time incl. 3 prep kernels)"

@@ -76,8 +76,8 @@ enum {
                                    stages, operands staged through registers               */
   B200FDTD_KERNEL_SYSTOLIC_ASYNC = 3, /* same protocol; operands staged through a cp.async
                                    shared-memory ring, service warp for the protocol       */
-  B200FDTD_KERNEL_SYSTOLIC_TMA = 4, /* same protocol; operands staged by TMA bulk copies
-                                   (cp.async.bulk + mbarrier) issued by the service warp    */
+  B200FDTD_KERNEL_RESERVED4 = 4, /* (was a TMA-staged variant: measured 17-28 Gcell/s against 76,
+                                   removed in round 2; the value is rejected)               */
   B200FDTD_KERNEL_SYSTOLIC_LEAN = 5 /* same protocol; one warp per column pair, no CTA barrier in
                                    the plane loop (fp32, z-column of exactly 32 vectors)     */
 };
@@ -149,9 +149,25 @@ int b200fdtd_run_host(const b200fdtd_desc* desc, const void* const* host_inputs,
  * buffers[0..6] = inputs in the order above, buffers[7] = output, buffers[8] = workspace
  * (declared by the python wrapper as a second, scratch result); `opaque` = the bytes of a
  * b200fdtd_desc.  Failures are reported through b200fdtd_last_error() and leave the output
- * untouched (XLA's legacy API has no status channel). */
+ * untouched (XLA's legacy API has no status channel: prefer the _status entry below). */
 void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
                               size_t opaque_len);
+
+/* The same call under XLA's status-returning convention (API_VERSION_STATUS_RETURNING,
+ * xla/service/custom_call_status.h): on failure the message of b200fdtd_last_error() is handed to
+ * XLA through XlaCustomCallStatusSetFailure (resolved from the host process at run time), so a bad
+ * descriptor or an undersized scratch buffer raises in Python instead of yielding an unwritten
+ * result.  `opaque` may carry, after the descriptor, a uint64 with the scratch bytes the wrapper
+ * declared at trace time; the run is refused when this device's plan needs more.  This is the
+ * entry INTEGRATION.md registers. */
+typedef struct b200fdtd_xla_status b200fdtd_xla_status;   /* = XlaCustomCallStatus */
+void b200fdtd_xla_custom_call_status(void* stream, void** buffers, const char* opaque,
+                                     size_t opaque_len, b200fdtd_xla_status* status);
+
+/* b200fdtd_run_host allocates from a private stream-ordered pool (one per device) that keeps its
+ * blocks between calls; this returns them to the driver.  The device's default pool is never
+ * touched. */
+int b200fdtd_host_pool_trim(int device);
 
 /* Introspection for tests/benchmarks: fills `info[8]` with what the AUTO policy would run for
  * `desc` on the current device: {kernel, tile_y, stages, threads, ctas, smem_bytes,

@@ -71,21 +71,27 @@ def local_problem(kw, rank, world):
     # channel 0 acts on global plane p, channel 1 on p-1; a rank keeps a channel only if the
     # plane it acts on is one of its OWNED planes (a hit on a ghost plane would be harmless --
     # the ghost is overwritten by the next exchange -- but masking keeps the intent explicit).
-    lp = (p - (x0 - 1)) % X                                  # local index of global plane p
-    lp1 = (p - 1 - (x0 - 1)) % X                             # ... and of plane p-1 (periodic)
+    # Ownership is decided on GLOBAL plane indices (a local modulo would map plane X-1 of a slab
+    # that covers the periodic wrap onto the low ghost instead of its owned copy).
+    g0, g1 = p % X, (p - 1) % X
+    own0, own1 = x0 <= g0 < x1, x0 <= g1 < x1
     wf = wf.copy()
-    own0 = 1 <= lp <= nloc
-    own1 = 1 <= lp1 <= nloc
-    if own1 and lp1 != lp - 1 and wf[:, 1].any():
-      # plane p-1 wraps around the periodic boundary onto a non-adjacent local plane
-      raise NotImplementedError("x source at plane 0 with an active second channel")
     if not own0:
       wf[:, 0] = 0
     if not own1:
       wf[:, 1] = 0
-    if not (own0 or own1) or lp > nloc + 1:
+    if own0 and own1:
+      lp = g0 - x0 + 1
+      if g1 - x0 + 1 != lp - 1 and wf[:, 1].any():
+        # the engine injects channel 1 on the plane before channel 0's; here the two owned planes
+        # are not adjacent in local coordinates (the slab covers the periodic wrap)
+        raise NotImplementedError("x source at plane 0 of a slab that also owns plane X-1")
+    elif own0:
+      lp = g0 - x0 + 1                                       # channel 1 (zeroed) lands on lp-1
+    elif own1:
+      lp = g1 - x0 + 2                                       # channel 0 (zeroed) lands on lp
+    else:
       lp = 1
-      wf[:] = 0
     loc["source_position"] = int(lp)
     loc["source_waveform"] = wf
     loc["source_field"] = sf

@@ -7,21 +7,21 @@
 #include "../../include/b200fdtd.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <string>
 
 #include "fdtd_common.cuh"
 #include "kernels_systolic.cuh"
 #include "kernels_systolic2.cuh"
-#include "kernels_systolic3.cuh"
 #include "kernels_lean.cuh"
-#include "kernels_lean1.cuh"
 #include "kernels_lean16.cuh"
 #include "kernels_twopass.cuh"
 #include "postproc.cuh"
@@ -51,6 +51,11 @@ static int fail(int code, const char* fmt, ...) {
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int num_outputs(const b200fdtd_desc* d) {
+  if (d->out_stop <= d->out_start) return 0;
+  return (d->out_stop - d->out_start + d->out_step - 1) / d->out_step;
+}
+
 static int validate(const b200fdtd_desc* d) {
   if (!d) return fail(B200FDTD_EINVAL, "desc is NULL");
   if (d->struct_bytes != sizeof(b200fdtd_desc) || d->abi_version != B200FDTD_ABI_VERSION)
@@ -72,22 +77,22 @@ static int validate(const b200fdtd_desc* d) {
   if (d->pml_lo < 0 || d->pml_hi < 0 || d->pml_lo + d->pml_hi > d->Z)
     return fail(B200FDTD_EINVAL, "pml_widths (%d,%d) do not fit Z=%d", d->pml_lo, d->pml_hi, d->Z);
   if (d->out_step < 1) return fail(B200FDTD_EINVAL, "output_steps step must be >= 1");
-  if (d->out_stop > d->out_start && (d->out_start < 0 || d->out_stop > d->tt + d->out_step - 1))
+  // every snapshot step must be a step the run performs: the last one is
+  // out_start + (n_out - 1) * out_step (oracle/fdtd_numpy.py rejects outs[-1] >= tt the same way)
+  if (d->out_stop > d->out_start &&
+      (d->out_start < 0 ||
+       (long long)d->out_start + (long long)(num_outputs(d) - 1) * d->out_step >= d->tt))
     return fail(B200FDTD_EINVAL, "output_steps (%d,%d,%d) outside [0,tt=%d)", d->out_start,
                 d->out_stop, d->out_step, d->tt);
   if (!(d->dt > 0.f) || !isfinite(d->dt)) return fail(B200FDTD_EINVAL, "dt must be > 0");
-  if (d->kernel < 0 || d->kernel > 5) return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
+  if (d->kernel < 0 || d->kernel > 5 || d->kernel == B200FDTD_KERNEL_RESERVED4)
+    return fail(B200FDTD_EINVAL, "unknown kernel %d", d->kernel);
   if (d->cols < 0 || d->cols > 2) return fail(B200FDTD_EINVAL, "cols must be 0, 1 or 2");
   if (d->proj_rows < 0 || d->proj_rows > 64)
     return fail(B200FDTD_EINVAL, "proj_rows must be in [0, 64], got %d", d->proj_rows);
   if (d->proj_rows > 0 && d->out_stop <= d->out_start)
     return fail(B200FDTD_EINVAL, "fused projection needs at least one output step");
   return B200FDTD_OK;
-}
-
-static int num_outputs(const b200fdtd_desc* d) {
-  if (d->out_stop <= d->out_start) return 0;
-  return (d->out_stop - d->out_start + d->out_step - 1) / d->out_step;
 }
 
 static Geom make_geom(const b200fdtd_desc* d) {
@@ -124,7 +129,7 @@ struct Plan {
 
 static bool is_systolic(int k) {
   return k == B200FDTD_KERNEL_SYSTOLIC || k == B200FDTD_KERNEL_SYSTOLIC_ASYNC ||
-         k == B200FDTD_KERNEL_SYSTOLIC_TMA || k == B200FDTD_KERNEL_SYSTOLIC_LEAN;
+         k == B200FDTD_KERNEL_SYSTOLIC_LEAN;
 }
 
 static int device_props(int* sms, int* l2_bytes) {
@@ -148,17 +153,6 @@ static bool configure_async(const Geom& g, const b200fdtd_desc* d, int depth, in
   return false;
 }
 
-template <typename T>
-static bool configure_tma(const Geom& g, const b200fdtd_desc* d, int depth, int sms, int l2,
-                          SystolicCfg* cfg, std::string* why) {
-  switch (depth) {
-    case 1: return systolic3_configure_d<T, 1>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
-    case 2: return systolic3_configure_d<T, 2>(g, d->tile_y, d->stages, d->threads, sms, l2, cfg, why);
-  }
-  *why = "prefetch must be 1 or 2";
-  return false;
-}
-
 // AUTO: the warp-per-column-pair kernel when the geometry allows it (fp32, 32 z-vectors), else the
 // cp.async-staged systolic kernel (prefetch distance 1 measured fastest: a deeper ring only
 // shrinks the tile), else the register-staged one, else the per-step kernels.
@@ -172,10 +166,8 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
   if (rc) return rc;
   std::string why;
   if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
-    bool ok = d->cols == 1
-        ? lean1_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why)
-        : lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why);
-    if (!ok && d->cols != 1 && g.Zq <= kL16ZR) {   // short columns / fp16 storage: half-warp variant
+    bool ok = lean_configure(g, sizeof(T) == 2, d->tile_y, d->stages, sms, l2, &plan->sys, &why);
+    if (!ok && g.Zq <= kL16ZR) {                   // short columns / fp16 storage: half-warp variant
       std::string why16;
       ok = lean16_configure<T>(g, d->tile_y, d->stages, sms, l2, &plan->sys, &why16);
       if (!ok) why += "; half-warp variant: " + why16;
@@ -183,13 +175,6 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
     if (!ok)
       return fail(B200FDTD_EUNSUPPORTED, "systolic_lean kernel unavailable: %s", why.c_str());
     plan->depth = 1;
-    return B200FDTD_OK;
-  }
-  if (d->kernel == B200FDTD_KERNEL_SYSTOLIC_TMA) {
-    const int depth = d->prefetch > 0 ? d->prefetch : 1;
-    if (!configure_tma<T>(g, d, depth, sms, l2, &plan->sys, &why))
-      return fail(B200FDTD_EUNSUPPORTED, "systolic_tma kernel unavailable: %s", why.c_str());
-    plan->depth = depth;
     return B200FDTD_OK;
   }
   if (d->kernel == B200FDTD_KERNEL_AUTO &&
@@ -439,14 +424,9 @@ static int run_typed(const b200fdtd_desc* d, const Geom& g, const Plan& plan, co
     if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC) rc = systolic_launch<T>(g, p, plan.sys, sync, st);
     else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_LEAN) {
       if (plan.sys.cols == 16) rc = lean16_launch<T>(g, p, plan.sys, sync, st);
-      else if constexpr (sizeof(T) == 4)
-        rc = plan.sys.cols == 1 ? lean1_launch(g, p, plan.sys, sync, st)
-                                : lean_launch(g, p, plan.sys, sync, st);
+      else if constexpr (sizeof(T) == 4) rc = lean_launch(g, p, plan.sys, sync, st);
       else rc = (int)cudaErrorInvalidValue;
     }
-    else if (plan.kernel == B200FDTD_KERNEL_SYSTOLIC_TMA)
-      rc = plan.depth == 2 ? systolic3_launch_d<T, 2>(g, p, plan.sys, sync, st)
-                           : systolic3_launch_d<T, 1>(g, p, plan.sys, sync, st);
     else if (plan.depth == 1) rc = systolic2_launch_d<T, 1>(g, p, plan.sys, sync, st);
     else if (plan.depth == 2) rc = systolic2_launch_d<T, 2>(g, p, plan.sys, sync, st);
     else rc = systolic2_launch_d<T, 3>(g, p, plan.sys, sync, st);
@@ -501,6 +481,37 @@ static int run_impl(const b200fdtd_desc* d, const void* const* in, void* const* 
                                 : run_typed<float>(d, g, plan, w, in, out, ws, st);
   if (own) cudaFreeAsync(ws, st);
   return rc;
+}
+
+// Private stream-ordered memory pool of b200fdtd_run_host, one per device, created on first use.
+// Its release threshold is unlimited so that freed blocks stay cached between calls; the
+// device's default pool (and therefore every other user of cudaMallocAsync in the process) is
+// left alone.  b200fdtd_host_pool_trim() hands the cached blocks back to the driver.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+static int host_pool(int device, cudaMemPool_t* out) {
+  if (device < 0 || device >= 64) return fail(B200FDTD_EINVAL, "device %d out of range", device);
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  if (!g_pools[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    CUDA_TRY(cudaMemPoolCreate(&pool, &props));
+    unsigned long long keep = ~0ull;
+    cudaError_t e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) {
+      cudaMemPoolDestroy(pool);
+      return fail(B200FDTD_ECUDA, "cudaMemPoolSetAttribute failed: %s", cudaGetErrorString(e));
+    }
+    g_pools[device] = pool;
+  }
+  *out = g_pools[device];
+  return B200FDTD_OK;
 }
 
 }  // namespace b200
@@ -569,8 +580,8 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
   void* ws = nullptr;
   rc = B200FDTD_OK;
   auto cleanup = [&]() {
-    // stream-ordered frees: the blocks go back to the device's default pool, whose release
-    // threshold is raised below so that the next call does not pay for fresh allocations
+    // stream-ordered frees: the blocks go back to the library's private pool, which keeps them
+    // cached so that the next call does not pay for fresh allocations
     for (auto p : din) if (p) cudaFreeAsync(p, st);
     if (dout[0]) cudaFreeAsync(dout[0], st);
     if (ws) cudaFreeAsync(ws, st);
@@ -585,22 +596,18 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
     }                                                                                       \
   } while (0)
   TRY_CLEAN(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  {
-    cudaMemPool_t pool = nullptr;
-    unsigned long long keep = ~0ull;               // keep freed blocks cached between calls
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    cudaGetLastError();
-  }
+  cudaMemPool_t pool = nullptr;
+  rc = host_pool(device, &pool);
+  if (rc) { cleanup(); return rc; }
   for (int i = 0; i < nin; ++i) {
     if (!hin[i]) { cleanup(); return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i); }
-    TRY_CLEAN(cudaMallocAsync(&din[i], bytes[i] ? bytes[i] : 4, st));
+    TRY_CLEAN(cudaMallocFromPoolAsync(&din[i], bytes[i] ? bytes[i] : 4, pool, st));
     TRY_CLEAN(cudaMemcpyAsync(din[i], hin[i], d->tt > 0 || i != B200FDTD_IN_SOURCE_WAVEFORM
                                                   ? bytes[i] : 0,
                               cudaMemcpyHostToDevice, st));
   }
-  TRY_CLEAN(cudaMallocAsync(&dout[0], out_bytes ? out_bytes : 4, st));
-  TRY_CLEAN(cudaMallocAsync(&ws, ws_bytes, st));
+  TRY_CLEAN(cudaMallocFromPoolAsync(&dout[0], out_bytes ? out_bytes : 4, pool, st));
+  TRY_CLEAN(cudaMallocFromPoolAsync(&ws, ws_bytes, pool, st));
   rc = run_impl(d, din, dout, ws, ws_bytes, st);
   if (rc == B200FDTD_OK && out_bytes) {
     if (!hout[0]) { cleanup(); return fail(B200FDTD_EINVAL, "outputs[0] is NULL"); }
@@ -612,22 +619,62 @@ int b200fdtd_run_host(const b200fdtd_desc* d, const void* const* hin, void* cons
   return rc;
 }
 
-void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
-                              size_t opaque_len) {
-  if (!buffers || !opaque || opaque_len != sizeof(b200fdtd_desc)) {
-    fail(B200FDTD_EINVAL, "custom call: opaque must be a b200fdtd_desc (%zu bytes), got %zu",
-         sizeof(b200fdtd_desc), opaque_len);
-    return;
-  }
+int b200fdtd_host_pool_trim(int device) {
+  if (device < 0 || device >= 64) return fail(B200FDTD_EINVAL, "device %d out of range", device);
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  if (g_pools[device]) CUDA_TRY(cudaMemPoolTrimTo(g_pools[device], 0));
+  return B200FDTD_OK;
+}
+
+// Body of both XLA custom-call entry points.  `opaque` is a b200fdtd_desc, optionally followed
+// by a uint64 = the scratch bytes the wrapper declared at trace time (b200fdtd_workspace_bytes
+// on the tracing device): the run is refused if this device's plan needs more.
+static int custom_call_impl(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
+  const size_t with_ws = sizeof(b200fdtd_desc) + sizeof(uint64_t);
+  if (!buffers || !opaque || (opaque_len != sizeof(b200fdtd_desc) && opaque_len != with_ws))
+    return fail(B200FDTD_EINVAL,
+                "custom call: opaque must be a b200fdtd_desc (%zu bytes) [+ uint64 scratch bytes], got %zu",
+                sizeof(b200fdtd_desc), opaque_len);
   b200fdtd_desc d;
   memcpy(&d, opaque, sizeof d);
+  int rc = validate(&d);
+  if (rc) return rc;
+  size_t ws_bytes = b200fdtd_workspace_bytes(&d);
+  if (ws_bytes == 0) return B200FDTD_EUNSUPPORTED;       // last_error already says why
+  if (opaque_len == with_ws) {
+    uint64_t declared;
+    memcpy(&declared, opaque + sizeof d, sizeof declared);
+    if (declared < ws_bytes)
+      return fail(B200FDTD_EWORKSPACE,
+                  "custom call: scratch declared at trace time (%llu bytes) is smaller than this "
+                  "device's plan needs (%zu bytes)", (unsigned long long)declared, ws_bytes);
+    ws_bytes = (size_t)declared;
+  }
   // operands: the 7 arrays (+ the projection matrix when proj_rows > 0), then result, scratch
   const int nin = d.proj_rows > 0 ? B200FDTD_MAX_INPUTS : B200FDTD_NUM_INPUTS;
   const void* ins[B200FDTD_MAX_INPUTS] = {nullptr};
   for (int i = 0; i < nin; ++i) ins[i] = buffers[i];
   void* outs[1] = {buffers[nin]};
-  const size_t ws_bytes = b200fdtd_workspace_bytes(&d);
-  run_impl(&d, ins, outs, buffers[nin + 1], ws_bytes, static_cast<cudaStream_t>(stream));
+  return run_impl(&d, ins, outs, buffers[nin + 1], ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+void b200fdtd_xla_custom_call(void* stream, void** buffers, const char* opaque,
+                              size_t opaque_len) {
+  custom_call_impl(stream, buffers, opaque, opaque_len);
+}
+
+void b200fdtd_xla_custom_call_status(void* stream, void** buffers, const char* opaque,
+                                     size_t opaque_len, b200fdtd_xla_status* status) {
+  const int rc = custom_call_impl(stream, buffers, opaque, opaque_len);
+  if (rc != B200FDTD_OK && status) {
+    // XlaCustomCallStatus is `struct { std::optional<std::string> message; }` on XLA's side and
+    // must be set through XlaCustomCallStatusSetFailure, which lives in the host process
+    // (jaxlib).  Resolve it at run time; without it the failure stays in last_error().
+    typedef void (*set_failure_fn)(void*, const char*, size_t);
+    static set_failure_fn set_failure =
+        reinterpret_cast<set_failure_fn>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+    if (set_failure) set_failure(status, g_last_error.c_str(), g_last_error.size());
+  }
 }
 
 int b200fdtd_plan_info(const b200fdtd_desc* desc, int64_t* info) {
@@ -911,8 +958,7 @@ int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stre
     rc = s->reduced ? lean16_launch<__half>(g, s->ph, s->plan.sys, sync, st)
                     : lean16_launch<float>(g, s->pf, s->plan.sys, sync, st);
   else
-    rc = s->plan.sys.cols == 1 ? lean1_launch(g, s->pf, s->plan.sys, sync, st)
-                               : lean_launch(g, s->pf, s->plan.sys, sync, st);
+    rc = lean_launch(g, s->pf, s->plan.sys, sync, st);
   if (rc != 0)
     return fail(B200FDTD_ECUDA, "systolic launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   return B200FDTD_OK;

@@ -40,7 +40,6 @@
 #include "fdtd_common.cuh"
 #include "kernels_systolic.cuh"
 #include "kernels_systolic2.cuh"
-#include "kernels_systolic3.cuh"
 
 namespace b200 {
 
@@ -76,10 +75,7 @@ __device__ __forceinline__ float4 arr_to_f4(const float (&v)[4]) {
 
 // U = unroll factor of the plane loop (2 removes the loop-carried register moves).
 // STATS = per-warp wait-time accounting printed at the end (debug builds of the plan only).
-// TMA = the ring is filled by bulk copies (cp.async.bulk + one mbarrier per slot) issued by one
-// elected lane per warp -- adjacent columns are contiguous in memory, so a plane costs ~14 copy
-// instructions per WARP instead of ~29 cp.async + addresses per LANE.
-template <int U, bool STATS, bool TMA>
+template <int U, bool STATS>
 __global__ void __launch_bounds__(32 * (kLeanMaxWarps + 1), 1)
 lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync) {
   constexpr int VW = 4;
@@ -103,12 +99,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
 
-  __shared__ unsigned long long lbar[kLeanMaxWarps][5];   // TMA: E slots 0..2, H/B slots 3..4
   if (tid < (int)(sizeof(LeanCtl) / sizeof(unsigned))) reinterpret_cast<unsigned*>(&ctl)[tid] = 0u;
-  if constexpr (TMA) {
-    if (tid < 5 * kLeanMaxWarps) mbar_init(&lbar[tid / 5][tid % 5], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
   if (tid == 0) ctl.ok = 1u;
   __syncthreads();
@@ -232,7 +223,6 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   long long st_cp = 0, st_avail = 0, st_next = 0, st_rc = 0, st_hc = 0;
   const long long st_begin = STATS ? clock64() : 0;
   bool ok = true;
-  unsigned phases = 0;                             // TMA: current parity of each ring-slot mbarrier
   unsigned kk = 0;                                 // cumulative iteration count (never reset)
   unsigned iters_done = 0;
 
@@ -394,123 +384,15 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       issue_h(PL, sh);
     };
 
-    // TMA flavour of issue(): executed by lane 0 only.  Columns A, B (and C) of a pair are
-    // adjacent in memory unless the pair straddles the periodic y wrap, so each array of a plane
-    // is one bulk copy of up to 3 x 512 B into consecutive ring rows; psi rows are copied whole
-    // (all PML groups of the column).  ie / ih = barrier index of the E slot / H-B slot.
-    auto issue_tma = [&](int PL, int PLn, float4* se, float4* sh, int ie, int ih, float4* se_first,
-                         int ie_first, bool ecoef) {
-      const unsigned vN = (unsigned)PLn * PVn, vP = (unsigned)PL * PVn;
-      const unsigned cA_ = (unsigned)yA * ZQ, cB_ = (unsigned)yB * ZQ, cC_ = (unsigned)yC * ZQ;
-      const bool adjAB = yB == yA + 1, adjBC = yC == yB + 1;
-      unsigned long long* const bar_e = &lbar[w][ie];
-      unsigned long long* const bar_h = &lbar[w][ih];
-      // copies `n` (1..3) columns starting at A into rows d, d+ZQ, d+2ZQ; returns the bytes
-      auto cols = [&](float4* d, const float4* src, unsigned v, int n, unsigned long long* bar) {
-        if (n == 3 && adjAB && adjBC) { tma_load_1d(d, src + (v + cA_), 1536, bar); return 1536u; }
-        if (n >= 2 && adjAB) {
-          tma_load_1d(d, src + (v + cA_), 1024, bar);
-          if (n == 3) tma_load_1d(d + 2 * ZQ, src + (v + cC_), 512, bar);
-          return n == 3 ? 1536u : 1024u;
-        }
-        tma_load_1d(d, src + (v + cA_), 512, bar);
-        if (n >= 2) {
-          if (n == 3 && adjBC) { tma_load_1d(d + ZQ, src + (v + cB_), 1024, bar); return 1536u; }
-          tma_load_1d(d + ZQ, src + (v + cB_), 512, bar);
-          if (n == 3) tma_load_1d(d + 2 * ZQ, src + (v + cC_), 512, bar);
-        }
-        return (unsigned)n * 512u;
-      };
-      const int nE = doHB ? 3 : 2, nEy = doHB ? 2 : 1, nH = doHB ? 2 : 1;
-      fence_proxy_async();                           // earlier generic reads of these slots are done
-      unsigned be_ = 0, bh_ = 0;
-      be_ += cols(se + 0 * ZQ, rEx, vN, nE, bar_e);
-      be_ += cols(se + 3 * ZQ, rEz, vN, nE, bar_e);
-      be_ += cols(se + 6 * ZQ, rEy, vN, nEy, bar_e);
-      mbar_expect_tx(bar_e, be_);
-      bh_ += cols(sh + 0 * ZQ, rHx, vP, nH, bar_h);
-      bh_ += cols(sh + 2 * ZQ, rHy, vP, nH, bar_h);
-      bh_ += cols(sh + 4 * ZQ, rHz, vP, nH, bar_h);
-      const unsigned pb = (unsigned)psi_row * 16u;   // psi bytes per column
-      float4* const ps = sh + kLeanHRows * ZQ;
-      const unsigned pp = (unsigned)PL * PPn;
-      const unsigned pA_ = (unsigned)yA * g.npg, pB_ = (unsigned)yB * g.npg;
-      auto pcols = [&](float4* d, const float4* src, int n, bool from_b) {
-        if (pb == 0) return 0u;
-        if (!from_b && n == 2 && adjAB) { tma_load_1d(d, src + (pp + pA_), 2 * pb, bar_h); return 2 * pb; }
-        unsigned got = 0;
-        if (!from_b) { tma_load_1d(d, src + (pp + pA_), pb, bar_h); got += pb; }
-        if (from_b || n == 2) { tma_load_1d(d + psi_row, src + (pp + pB_), pb, bar_h); got += pb; }
-        return got;
-      };
-      bh_ += pcols(ps, rPx, nH, false);
-      bh_ += pcols(ps + 2 * psi_row, rPy, nH, false);
-      if (ecoef) {
-        if (ownA) {
-          bh_ += cols(sh + 6 * ZQ, Bx, vP, nH, bar_h);
-          bh_ += cols(sh + 8 * ZQ, By, vP, nH, bar_h);
-          bh_ += cols(sh + 10 * ZQ, Bz, vP, nH, bar_h);
-          bh_ += pcols(ps + 4 * psi_row, ePx, nH, false);
-          bh_ += pcols(ps + 6 * psi_row, ePy, nH, false);
-          tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row, A4 + ((unsigned)PL * (unsigned)Y + yA), 16, bar_h);
-          bh_ += 16;
-          if (zsrc) {
-            tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 2, S4 + ((unsigned)PL * (unsigned)Y + yA), 16, bar_h);
-            bh_ += 16;
-          }
-        } else if (doHB) {                           // warp 0: only column B is owned
-          tma_load_1d(sh + 7 * ZQ, Bx + (vP + cB_), 512, bar_h);
-          tma_load_1d(sh + 9 * ZQ, By + (vP + cB_), 512, bar_h);
-          tma_load_1d(sh + 11 * ZQ, Bz + (vP + cB_), 512, bar_h);
-          bh_ += 1536;
-          bh_ += pcols(ps + 4 * psi_row, ePx, 1, true);
-          bh_ += pcols(ps + 6 * psi_row, ePy, 1, true);
-        }
-        if (doHB) {
-          tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 1, A4 + ((unsigned)PL * (unsigned)Y + yB), 16, bar_h);
-          bh_ += 16;
-          if (zsrc) {
-            tma_load_1d(sh + kLeanHRows * ZQ + 8 * psi_row + 3, S4 + ((unsigned)PL * (unsigned)Y + yB), 16, bar_h);
-            bh_ += 16;
-          }
-        }
-      }
-      mbar_expect_tx(bar_h, bh_);
-      if (se_first) {                                // very first plane of the sweep: E[PL] too
-        unsigned long long* const bar_f = &lbar[w][ie_first];
-        unsigned bf_ = 0;
-        bf_ += cols(se_first + 0 * ZQ, rEx, vP, nE, bar_f);
-        bf_ += cols(se_first + 3 * ZQ, rEz, vP, nE, bar_f);
-        bf_ += cols(se_first + 6 * ZQ, rEy, vP, nEy, bar_f);
-        mbar_expect_tx(bar_f, bf_);
-      }
-    };
-    // spin on the mbarrier of a ring slot (all lanes; warp-uniform)
-    auto wait_slot = [&](int idx, unsigned& phases) -> bool {
-      unsigned long long* const bar = &lbar[w][idx];
-      const unsigned par = (phases >> idx) & 1u;
-      const bool r = spin([&]() { return mbar_try_wait(bar, par); });
-      phases ^= 1u << idx;
-      return r;
-    };
-
     int P = wrapi(cstart - 1, X);                  // plane of iteration i (i = 0: prologue plane)
     float4* sprev = wbase;                         // slot holding E[P]
     float4* scur = wbase + eslot_f4;               // slot holding E[P+1]
     float4* snext = wbase + 2 * eslot_f4;          // slot being filled with E[P+2]
     float4* hcur = hbase;                          // slot holding H, B, psi, absorber row of P
     float4* hnext = hbase + hslot_f4;              // ... being filled for P+1
-    int ie_prev = 0, ie_cur = 1, ie_next = 2, ih_cur = 3, ih_next = 4;   // barrier index of each slot
     ok = wait_deps(0);
-    if constexpr (TMA) {
-      __syncwarp();                                // previous sweep's reads of the ring are done
-      if (ok && lane == 0)
-        issue_tma(P, P + 1 == X ? 0 : P + 1, scur, hcur, ie_cur, ih_cur, sprev, ie_prev, false);
-      if (ok) ok = wait_slot(ie_prev, phases);     // E[P]
-    } else {
-      if (ok) issue(P, P + 1 == X ? 0 : P + 1, scur, hcur, sprev, false);
-      cp_async_commit();
-    }
+    if (ok) issue(P, P + 1 == X ? 0 : P + 1, scur, hcur, sprev, false);
+    cp_async_commit();
 
     float hypA[VW], hzpA[VW], hypB[VW], hzpB[VW];  // H^{n+1/2}[P-1] of the thread's own cells
 #pragma unroll
@@ -526,25 +408,13 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         cp_async_wait<0>();
         st_cp += clock64() - c0;
       }
-      if constexpr (TMA) {
-        ok = wait_slot(ie_cur, phases) && wait_slot(ih_cur, phases);   // E[P+1], H/B/psi[P] landed
+      cp_async_wait<0>();                          // this lane's copies of iteration i have landed
+      if (i < X) {
+        ok = wait_deps(i + 1);
         if (!ok) break;
-        if (i < X) {
-          ok = wait_deps(i + 1);
-          if (!ok) break;
-          __syncwarp();                            // every lane is done with the slots being refilled
-          if (lane == 0)
-            issue_tma(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, hnext, ie_next, ih_next, nullptr, 0, true);
-        }
-      } else {
-        cp_async_wait<0>();                        // this lane's copies of iteration i have landed
-        if (i < X) {
-          ok = wait_deps(i + 1);
-          if (!ok) break;
-          issue_e(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, nullptr);
-        }
-        __syncwarp();                              // the absorber rows were copied by lanes 0, 1
+        issue_e(Pn, Pn + 1 == X ? 0 : Pn + 1, snext, nullptr);
       }
+      __syncwarp();                                // the absorber rows were copied by lanes 0, 1
       if (w == 0 && lane == 0) st_vol_s(&ctl.front, iters_done + (unsigned)i);
       // The field vectors that have just landed (E^n[P+1], H^{n-1/2}[P]) have now been read by
       // their only reader -- columns 2 .. Yt-1 are loaded by no other tile, and every plane but
@@ -614,10 +484,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
                  ikh[v], dt, psxB[v], psyB[v], hxB[v], hyB[v], hzB[v]);
         }
       }
-      if constexpr (!TMA) {                        // second half of the copies for iteration i + 1
-        if (i < X) issue_h(Pn, hnext);
-        cp_async_commit();
-      }
+      if (i < X) issue_h(Pn, hnext);               // second half of the copies for iteration i + 1
+      cp_async_commit();
       // boundary H for the next warp: wait until it has consumed the slot's previous content
       {
         float4* const xs = xmine + (kk & (kLeanXR - 1)) * 2 * ZQ;
@@ -730,8 +598,6 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       P = Pn;
       float4* const tmp = sprev; sprev = scur; scur = snext; snext = tmp;
       float4* const tmh = hcur; hcur = hnext; hnext = tmh;
-      { const int t3 = ie_prev; ie_prev = ie_cur; ie_cur = ie_next; ie_next = t3; }
-      { const int t2 = ih_cur; ih_cur = ih_next; ih_next = t2; }
       ++kk;
     }
     cp_async_wait<0>();
@@ -751,11 +617,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
 }
 
 inline const void* lean_fn(int unroll, bool stats) {
-  if (stats) return (const void*)lean_kernel<1, true, false>;
-  if (const char* e = getenv("B200FDTD_LEAN_TMA"))
-    if (atoi(e) != 0) return (const void*)lean_kernel<1, false, true>;
-  return unroll == 2 ? (const void*)lean_kernel<2, false, false>
-                     : (const void*)lean_kernel<1, false, false>;
+  if (stats) return (const void*)lean_kernel<1, true>;
+  return unroll == 2 ? (const void*)lean_kernel<2, false> : (const void*)lean_kernel<1, false>;
 }
 
 // Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.

@@ -68,6 +68,11 @@ inline cudaError_t adjoint_reduce_launch(const AdjFields& f, const float2* coef,
   const size_t cap = (size_t)sms * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  if (smem > 48 * 1024) {                          // up to 16 ports x 64 frequencies = 128 KB
+    const cudaError_t e = cudaFuncSetAttribute(adjoint_reduce_kernel<NP>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   adjoint_reduce_kernel<NP><<<(unsigned)blocks, 256, smem, st>>>(f, coef, ww, nvox, out);
   return cudaGetLastError();
 }

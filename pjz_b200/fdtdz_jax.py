@@ -10,7 +10,7 @@ current stream and the result is a CUDA tensor) or anything ``np.asarray`` accep
 ``b200fdtd_run_host`` copies up, runs, copies the snapshots back; the result is a NumPy array).
 
 ``launch_params`` (opaque in pjz, ``SimParams.launch_params`` :53) may be ``None`` or a dict with
-any of ``kernel`` ("auto" | "twopass" | "systolic" | "systolic_async" | "systolic_tma"),
+any of ``kernel`` ("auto" | "twopass" | "systolic" | "systolic_async"),
 ``tile_y``, ``stages``,
 ``threads``, ``prefetch``.
 To make ``import fdtdz_jax`` resolve to this module: ``pjz_b200.fdtdz_jax.install()``.
@@ -28,7 +28,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200fdtd.so")
 
 NUM_INPUTS = 7
-_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2, "systolic_async": 3, "systolic_tma": 4,
+_KERNELS = {"auto": 0, "twopass": 1, "systolic": 2, "systolic_async": 3,
             "systolic_lean": 5}
 ABI_VERSION = 1
 

@@ -94,6 +94,29 @@ def test_wrapper_shape_errors(built):
     fdtdz_jax.make_desc(**bad)
 
 
+@pytest.mark.parametrize("steps,ok", [((2, 12, 3), False), ((3, 13, 4), False), ((2, 11, 3), True),
+                                      ((9, 10, 1), True), ((10, 11, 1), False), ((0, 10, 1), True)])
+def test_last_snapshot_must_be_a_step_of_the_run(built, steps, ok):
+  """tt = 10: a snapshot at step >= tt would never be written ((2,12,3) -> [2,5,8,11]
+  used to be accepted); the NumPy oracle rejects the same inputs."""
+  from oracle import fdtd_numpy
+  kw = random_problem(tt=10, output_steps=steps)
+  lib = fdtdz_jax.lib()
+  d = fdtdz_jax.make_desc(**{**kw, "output_steps": (2, 9, 3)})
+  d.out_start, d.out_stop, d.out_step = steps
+  assert (lib.b200fdtd_validate(ctypes.byref(d)) == 0) == ok
+  if not ok:
+    assert "output_steps" in lib.b200fdtd_last_error().decode()
+    with pytest.raises(ValueError):
+      fdtd_numpy.fdtdz(**kw)
+
+
+def test_removed_kernel_value_is_rejected(built):
+  d = fdtdz_jax.make_desc(**random_problem())
+  d.kernel = 4                                  # was the TMA-staged variant (removed in round 2)
+  assert fdtdz_jax.lib().b200fdtd_validate(ctypes.byref(d)) == 1
+
+
 def test_output_count(built):
   kw = random_problem(tt=30, output_steps=(4, 30, 7))
   d = fdtdz_jax.make_desc(**kw)

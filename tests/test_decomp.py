@@ -215,6 +215,30 @@ def test_slab_inputs():
     local_problem(kw, 0, 12)
 
 
+def test_x_source_on_plane_zero_of_a_slab_that_owns_the_wrap():
+  """with one rank the slab owns plane 0 AND plane X-1; ownership of channel 1's plane
+  (p-1) % X must come from the global index.  An active second channel there cannot be injected
+  by one local plane pair and must raise instead of vanishing silently; a silent channel works."""
+  from oracle import fdtd_numpy
+  from pjz_b200._decomp import fdtdz_decomposed, local_problem
+  from tests.problems import random_problem
+  kw = random_problem(domain=(9, 7, 8), axis=0, tt=9, seed=5, src_pos=0, output_steps=(3, 9, 2))
+  with pytest.raises(NotImplementedError):
+    local_problem(kw, 0, 1)
+  quiet = dict(kw)
+  quiet["source_waveform"] = kw["source_waveform"].copy()
+  quiet["source_waveform"][:, 1] = 0
+  loc, nloc, _ = local_problem(quiet, 0, 1)
+  assert loc["source_position"] == 1 and loc["source_waveform"][:, 0].any()
+  out = fdtdz_decomposed(**quiet, make_slab=OracleSlab).numpy()
+  np.testing.assert_array_equal(out, fdtd_numpy.fdtdz(**quiet))
+  # two ranks: channel 1's plane X-1 belongs to the LAST rank, channel 0's plane 0 to the first
+  a, _, _ = local_problem(kw, 0, 2)
+  b, nb, _ = local_problem(kw, 1, 2)
+  assert a["source_position"] == 1 and a["source_waveform"][:, 0].any() and not a["source_waveform"][:, 1].any()
+  assert b["source_position"] == nb + 1 and b["source_waveform"][:, 1].any() and not b["source_waveform"][:, 0].any()
+
+
 # ---- GPU ------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu

@@ -25,7 +25,7 @@ from tests.problems import random_problem, rel_l2
 pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "engine_golden.npz"))
-KERNELS = ["twopass", "systolic", "systolic_async", "systolic_tma"]
+KERNELS = ["twopass", "systolic", "systolic_async"]
 FP32_TOL = 1e-5
 
 
@@ -116,16 +116,6 @@ def test_systolic_async_one_column_per_thread(domain, pml):
                                   fdtd_c.fdtdz(**kw))
 
 
-@pytest.mark.parametrize("prefetch", [1, 2])
-@pytest.mark.parametrize("tile_y,stages", [(1, 2), (3, 5), (6, 3), (4, 40)])
-def test_systolic_tma_tilings(tile_y, stages, prefetch):
-  kw = random_problem(domain=(11, 23, 16), axis=1, pml=(4, 4), tt=45, seed=13,
-                      output_steps=(20, 45, 6))
-  want = fdtd_c.fdtdz(**kw)
-  out = run_gpu(kw, kernel="systolic_tma", tile_y=tile_y, stages=stages, prefetch=prefetch)
-  np.testing.assert_array_equal(out, want)
-
-
 @pytest.mark.parametrize("axis", [0, 1, 2])
 @pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (6, 3), (4, 40), (13, 2)])
 def test_systolic_lean_tilings(tile_y, stages, axis):
@@ -146,27 +136,6 @@ def test_systolic_lean_ragged_domains(domain, pml, zb):
     kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
                         seed=7, output_steps=(5, 14, 4), absorb_pad=2, z_as_batch=zb)
     np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean"), fdtd_c.fdtdz(**kw))
-
-
-@pytest.mark.parametrize("axis", [0, 1, 2])
-@pytest.mark.parametrize("tile_y,stages", [(0, 0), (1, 2), (2, 3), (3, 5), (7, 3), (4, 40), (14, 2)])
-def test_systolic_lean_one_column_per_warp(tile_y, stages, axis):
-  """cols=1: one y-column per warp (15 compute warps), single coefficient slot refilled at the
-  end of each iteration."""
-  kw = random_problem(domain=(11, 23, 128), axis=axis, pml=(16, 16), tt=45, seed=13,
-                      output_steps=(20, 45, 6))
-  want = fdtd_c.fdtdz(**kw)
-  out = run_gpu(kw, kernel="systolic_lean", cols=1, tile_y=tile_y, stages=stages)
-  np.testing.assert_array_equal(out, want)
-
-
-@pytest.mark.parametrize("domain,pml,zb", [((9, 14, 125), (3, 5), False), ((16, 1, 128), (0, 0), False),
-                                           ((12, 26, 128), (0, 0), True), ((3, 30, 126), (16, 16), False)])
-def test_systolic_lean_one_column_ragged_domains(domain, pml, zb):
-  for axis in (0, 2):
-    kw = random_problem(domain=domain, sub=domain, offset=(0, 0, 0), axis=axis, pml=pml, tt=14,
-                        seed=7, output_steps=(5, 14, 4), absorb_pad=2, z_as_batch=zb)
-    np.testing.assert_array_equal(run_gpu(kw, kernel="systolic_lean", cols=1), fdtd_c.fdtdz(**kw))
 
 
 def test_systolic_lean_rejects_other_geometries():
@@ -318,9 +287,7 @@ def test_schedule_selection_and_linearity_large():
   b = run_gpu(kw, kernel="systolic")
   np.testing.assert_array_equal(a, b)
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_async"))
-  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_tma"))
   np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean"))
-  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean", cols=1))
   assert np.isfinite(a).all() and np.abs(a).max() > 0
   kw2 = dict(kw); kw2["output_steps"] = (5, 16, 10)
   np.testing.assert_array_equal(run_gpu(kw2), a[1:4:2])
@@ -416,7 +383,7 @@ def test_field_through_cuda_engine_matches_oracle_engine():
 
 @pytest.mark.parametrize("kernel,domain,pml", [
     ("twopass", (12, 10, 16), (3, 4)), ("systolic", (12, 10, 16), (3, 4)),
-    ("systolic_async", (14, 11, 24), (4, 4)), ("systolic_tma", (12, 10, 16), (3, 4)),
+    ("systolic_async", (14, 11, 24), (4, 4)),
     ("systolic_lean", (9, 21, 128), (16, 16)), ("auto", (7, 30, 126), (4, 6))])
 def test_fused_projection_is_bit_exact(kernel, domain, pml):
   """``output_projection``: the kernels accumulate W[:, s] * snapshot_s in place at every output
@@ -539,4 +506,3 @@ def test_lean_long_run_matches_independent_kernel_at_baseline_size():
   assert fdtdz_jax.plan_info(**{**kw, "launch_params": None})["kernel"] == "systolic_lean"
   np.testing.assert_array_equal(a, b)
   assert np.isfinite(a).all() and np.abs(a[-1]).max() > 0
-  np.testing.assert_array_equal(a, run_gpu(kw, kernel="systolic_lean", cols=1))
