@@ -35,10 +35,12 @@ def straight_waveguide(xx=64, yy=64, zz=64, width=12, thick=4, pad=16, pml=(8, 8
   yc, zc = yy / 2, zz / 2
   eps = _yee(lambda x, y, z: (np.abs(y - yc) < width / 2) & (np.abs(z - zc) < thick / 2) & (x > -1),
              xx, yy, zz)
+  # absorber: quadratic profile peaking at 1e-3 * pad^2 = 0.26 per unit time (|S11| = 0.026 on the
+  # C oracle; 4e-4 left 0.13 of reflection from the x ends); ports 35 cells apart
   params = SimParams(omega_range=(OMEGA0, OMEGA0), tt=tt, dt=dt, absorption_padding=pad,
-                     absorption_coeff=4e-4, pml_widths=pml, use_reduced_precision=reduced,
+                     absorption_coeff=1e-3, pml_widths=pml, use_reduced_precision=reduced,
                      domain_zz=zz + sum(pml))
-  ports = [("x", 8, True), ("x", xx - 10, True)]
+  ports = [("x", 10, True), ("x", 45, False)]
   return eps, ports, params, np.array([OMEGA0])
 
 
