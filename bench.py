@@ -54,6 +54,12 @@ def parse():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  ap.add_argument("--no-decomp", action="store_true",
+                  help="skip the domain-decomposed (cfg5 metalens, y-slabs) record")
+  ap.add_argument("--decomp-tt", type=int, default=2000)
+  ap.add_argument("--decomp-cols", type=int, default=512, help="owned y-columns per GPU")
+  ap.add_argument("--decomp-x", type=int, default=4096)
+  ap.add_argument("--decomp-transport", default="auto", choices=["auto", "p2p", "nccl"])
   return ap.parse_args()
 
 
@@ -234,6 +240,160 @@ def run_reference(args, rank, world):
   }))
 
 
+# ---- the sharded-domain configuration (BASELINE.json config 5) ------------------------------------
+
+def _metalens_slab(total, rank, world, ghost, tt, device, seed_wave=None):
+  """Engine kwargs of ONE rank's y-slab of the cfg5 metalens (`ghost` ghost columns per side),
+  built on the device: (local kwargs, owned columns, crop) as pjz_b200._decomp.local_problem_y
+  would return them from the global arrays, which are never materialised."""
+  import torch
+  from pjz_b200 import _field as glue
+  from pjz_b200 import workloads as W
+  from pjz_b200._decomp import slab_bounds
+  X, Y, Z = total
+  pad, pml = 32, (16, 16)
+  yy, zz = Y - 2 * pad, Z - sum(pml)
+  y0, y1 = slab_bounds(Y, world, rank)
+  cols = np.arange(y0 - ghost, y1 + ghost) % Y
+  eps = W.metalens_columns(total, np.clip(cols - pad, 0, yy - 1), device, pad=pad, pml=pml)
+  mask = glue._absorption_mask(X, Y, pad, 1e-4)
+  t = np.arange(tt)
+  rs = glue._ramped_sin(np.array([W.OMEGA0]), 4.0, 4.0, 0.5, tt)
+  wf = np.stack([rs.imag[:, 0] if rs.ndim == 2 else rs.imag, rs.real[:, 0] if rs.ndim == 2 else rs.real], -1)
+  # z-plane plane-wave source in the substrate (quadrature pair on Ex), as field() builds it
+  src = torch.zeros((2, 2, X, len(cols), 1), dtype=torch.float32, device=device)
+  src[1, 0] = 0.01
+  loc = dict(
+      epsilon=eps, dt=0.5, source_field=src, source_waveform=wf.astype(np.float32),
+      source_position=pml[0] + zz // 6, absorption_mask=np.ascontiguousarray(mask[:, :, cols]),
+      pml_kappa=np.ones((Z, 2), np.float32), pml_sigma=glue._pml_sigma(pml, Z, 0.5, 1.3),
+      pml_alpha=np.full((Z, 2), 0.05, np.float32), pml_widths=pml,
+      output_steps=(tt - 1, tt, 1), use_reduced_precision=False, launch_params=None,
+      offset=(pad, 0, pml[0]))
+  g0, g1 = max(pad, y0), min(pad + yy, y1)
+  crop = (g0 - y0 + ghost, g1 - y0 + ghost, g0 - pad, g1 - pad) if g1 > g0 else None
+  return loc, y1 - y0, crop
+
+
+def _decomp_check(rank, world, transport):
+  """Small domain, every rank: the N-rank decomposed result against the one-call engine."""
+  import torch
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import fdtdz_decomposed_p2p, fdtdz_decomposed_y
+  from tests.problems import random_problem
+  kw = random_problem(domain=(48, 32 * world, 128), axis=2, pml=(16, 16), tt=60, seed=321,
+                      output_steps=(20, 60, 13), absorb_pad=6, absorb_coeff=1e-3)
+  if transport == "p2p":
+    got = fdtdz_decomposed_p2p(**kw)
+  else:
+    got = fdtdz_decomposed_y(**kw, ghost=None if world > 1 else 8)
+  dev = dict(kw)
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  want = fdtdz_jax.fdtdz(**dev)
+  same = bool(torch.equal(got, want)) and bool(torch.isfinite(want).all()) and float(want.abs().max()) > 0
+  return "bit-exact" if same else "MISMATCH"
+
+
+def run_decomp(args, rank, world, local):
+  """BASELINE.json config 5: the metalens domain cut into y-slabs, one per GPU, weak scaling
+  (`--decomp-cols` owned columns x `--decomp-x` planes x 128 per GPU: 4096x4096x128 at 8 GPUs),
+  `--decomp-tt` steps.  Transport "p2p": halo exchange from inside the persistent kernel through
+  peer-mapped memory (one launch per GPU); "nccl": ghost zones + one packed send/recv per G steps.
+  Also times the SAME slab wrapped onto itself on one GPU (no neighbour) for the efficiency."""
+  import torch
+  import torch.distributed as dist
+  from pjz_b200._decomp import P2PSlabRun, YSlabRun, choose_ghost
+  dev = torch.device("cuda", local)
+  X, cols, Z, tt = args.decomp_x, args.decomp_cols, 128, args.decomp_tt
+  total = (X, cols * world, Z)
+  cells = X * cols * Z
+
+  def agree(ok):
+    f = torch.tensor([int(ok)], device=dev)
+    if world > 1:
+      dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    return bool(f.item())
+
+  def build(transport, r, w, steps):
+    if transport == "p2p":
+      loc, nloc, crop = _metalens_slab((X, cols * w, Z), r, w, 1, steps, dev)
+      return P2PSlabRun(None, local=(loc, nloc, crop), solo=(w != world))
+    shapes = dict(absorption_mask=np.broadcast_to(np.float32(0), (3, X, cols * w)),
+                  epsilon=np.broadcast_to(np.float32(0), (3, X - 64, cols * w - 64, Z - 32)),
+                  source_field=np.broadcast_to(np.float32(0), (2, 2, X, cols * w, 1)),
+                  pml_kappa=np.ones((Z, 2), np.float32), source_position=32, offset=(32, 32, 16),
+                  dt=0.5, source_waveform=np.zeros((steps, 2), np.float32),
+                  pml_sigma=np.zeros((Z, 2), np.float32), pml_alpha=np.zeros((Z, 2), np.float32),
+                  pml_widths=(16, 16), output_steps=(steps - 1, steps, 1),
+                  use_reduced_precision=False, launch_params=None)
+    G = choose_ghost(shapes, w)
+    loc, nloc, crop = _metalens_slab((X, cols * w, Z), r, w, G, steps, dev)
+    kw = dict(shapes, epsilon=np.zeros((3, X - 64, cols * w - 64, 0), np.float32))
+    run = YSlabRun(kw, ghost=G, local=(loc, nloc, crop), solo=(w != world))
+    run.tt = steps
+    return run
+
+  transport = args.decomp_transport
+  note = None
+  if transport in ("auto", "p2p"):
+    try:
+      probe = build("p2p", rank, world, 8)
+      probe.run(); torch.cuda.synchronize(); probe.close()
+      ok = True
+    except Exception as e:                                   # noqa: BLE001
+      ok, note = False, f"p2p unavailable: {str(e)[:160]}"
+    if agree(ok):
+      transport = "p2p"
+    elif transport == "p2p":
+      raise RuntimeError(note or "p2p transport failed on another rank")
+    else:
+      transport = "nccl"
+  check = _decomp_check(rank, world, transport)
+
+  def timed(w_, r_):
+    warm = build(transport, r_, w_, 64)
+    warm.run(); torch.cuda.synchronize(); warm.close(); del warm
+    run = build(transport, r_, w_, tt)
+    torch.cuda.synchronize()
+    if w_ > 1:
+      dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run.run(); b.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    lo, hi, snaps = run.local_snapshots()
+    chk = float(snaps.double().abs().sum().item())
+    ghost, kernel, stages = run.G, run.slab.kernel, run.slab.stages
+    run.close()
+    return ms, chk, ghost, kernel, stages
+
+  ms_n, chk, ghost, kernel, stages = timed(world, rank)
+  if world > 1:
+    dist.all_reduce(ms_n, op=dist.ReduceOp.MAX)
+  value_n = world * cells * tt / (float(ms_n.item()) / 1e3) / 1e9
+  # the same slab on ONE GPU, wrapped onto itself (every rank times its own; rank 0's is quoted)
+  if world > 1:
+    ms_1, _, _, _, _ = timed(1, 0)
+    value_1 = cells * tt / (float(ms_1.item()) / 1e3) / 1e9
+  else:
+    value_1 = value_n
+  assert np.isfinite(chk) and chk > 0, "decomposed run produced an empty/non-finite field"
+  return {
+      "value": value_n, "unit": UNIT, "n_gpus": world, "scaling": "weak",
+      "config": {"workload": f"cfg5 metalens {X}x{cols * world}x{Z} total grid, y-slabs of {cols} "
+                             f"columns per GPU, {tt} steps, fp32", "grid": [X, cols * world, Z],
+                 "fdtd_steps": tt, "kernel": f"{kernel}, {stages} stages"},
+      "ms_per_run": float(ms_n.item()), "value_1gpu_same_slab": value_1,
+      "efficiency_vs_1gpu": value_n / (world * value_1),
+      "transport": ("peer-mapped stores + release flags from inside the persistent kernel "
+                    "(CUDA IPC over NVLink), one launch per GPU, no host-driven exchange"
+                    if transport == "p2p" else
+                    f"NCCL send/recv of {ghost} ghost columns per side every {ghost} steps"),
+      "ghost": ghost, "exchange_ms": None if transport == "p2p" else "not separated",
+      "decomp_check": check, "note": note,
+  }
+
+
 def main():
   args = parse()
   rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +480,13 @@ def main():
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes)}
     assert np.isfinite(res).all()
 
+  # ---- the sharded-domain record (all ranks take part) ----------------------------------------------
+  decomp = None
+  if not args.no_decomp:
+    del out, dev
+    torch.cuda.empty_cache()
+    decomp = run_decomp(args, rank, world, local)
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -371,7 +538,7 @@ def main():
                          "inputs larger than L2, no flush needed")),
                  "plan": info},
       "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-      "clocks": clocks,
+      "clocks": clocks, "decomp": decomp,
   }
   print(json.dumps(line))
   if world > 1:

@@ -187,6 +187,24 @@ int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* 
                             const void* coef, void* out, void* stream);
 
 
+/* ---- Snapshot projection and port overlaps ---------------------------------------------------------
+ * b200fdtd_project: the phasor extraction of /root/reference/src/pjz/_field.py:272-279
+ * (`einsum("ij,j...->i...", pinv(phases.T), fields)`, then `outputs[:ww] + 1j * outputs[ww:]`) in
+ * one pass over the snapshots.  snapshots (n_out, nvox) float32 = the engine's output; weights
+ * (2*ww, n_out) float32 row-major = the pseudo-inverse; out (ww, nvox) complex64.  Device pointers,
+ * asynchronous on `stream`.
+ * b200fdtd_overlaps: the two-plane mode overlaps of :305-338 for every (field, port) pair at once:
+ *   vals[f][m][k][w] = sum_{c<2, u, v} modes[m][w][c][u][v] * fields[f][w][comp_c][plane k of port m]
+ * fields[f] (ww, 3, xx, yy, zz) complex64; modes[m] (ww, 2, U, V) complex64 on the plane normal to
+ * axes[m] (the two transverse components in ascending order); planes (nports, 2) int32 HOST array;
+ * vals (nfields, nports, 2, ww) complex64 device.  nfields, nports <= 16. */
+int b200fdtd_project(int ww, int n_out, size_t nvox, const void* snapshots, const void* weights,
+                     void* out, void* stream);
+int b200fdtd_overlaps(int nfields, int nports, int ww, int xx, int yy, int zz,
+                      const void* const* fields, const void* const* modes, const int* axes,
+                      const int* planes, void* vals, void* stream);
+
+
 /* ---- Waveguide-mode operator --------------------------------------------------------------------
  * y = op(x): the shifted waveguide operator of /root/reference/src/pjz/_mode.py:22-51 applied to
  * all ww frequencies and mm trial vectors in one launch (the body of pjz.mode's subspace
@@ -266,6 +284,40 @@ int b200fdtd_session_advance(b200fdtd_session* session, int n0, int nsteps, void
  *   [11] byte offset of psiH[0] of set 1 (-1: single set)      [12] psi floats per column
  *   [13] 1 if the state is ping-ponged (systolic session)      [14] kernel   [15] stages */
 int b200fdtd_session_layout2(const b200fdtd_session* session, int64_t* info);
+
+/* ---- y-slab sessions: halo exchange from inside the kernel over peer-mapped memory ---------------
+ * Domain decomposition along y for one process per GPU (pjz_b200/_decomp.py:P2PSlabRun; there is
+ * no reference counterpart).  The local domain of `desc` has Y = owned columns + 2: the tiles of
+ * the persistent kernel cover the owned columns [ylo, yhi) = [1, Y-1) and the columns 0 and Y-1 are
+ * ghosts that the NEIGHBOURING GPUs fill: every time step, the warp that owns a slab's edge column
+ * stores its new fields also into the neighbour's ghost column (peer-mapped stores over NVLink)
+ * and the edge tile's progress counter into the neighbour's mirror slot (st.release.sys), so the
+ * neighbour's edge tiles depend on them exactly as on a local tile.  One launch advances any
+ * number of steps; nothing is exchanged by the host.  Requirements: fp32 storage, 125 <= Z <= 128
+ * (the warp-per-column-pair kernel); every rank uses the same local shape and launch parameters;
+ * every workspace is mapped into its two neighbours' address space (CUDA IPC or a VMM export --
+ * the caller's business; pass the local base for a neighbour that is this rank itself).
+ *   1. b200fdtd_session_workspace_bytes_slab / _create_slab   (as the plain versions, + the range)
+ *   2. exchange workspace addresses; b200fdtd_session_set_peers(session, low, high)
+ *   3. per launch: barrier; b200fdtd_session_slab_reset; barrier; b200fdtd_session_advance.
+ *      (The first barrier says every rank has finished its previous launch -- a neighbour still
+ *      running would see its mirror slots cleared, or its ghosts overwritten, under its feet.) */
+size_t b200fdtd_session_workspace_bytes_slab(const b200fdtd_desc* desc, int ylo, int yhi);
+int b200fdtd_session_create_slab(const b200fdtd_desc* desc, const void* const* inputs,
+                                 void* const* outputs, void* workspace, size_t workspace_bytes,
+                                 void* stream, int ylo, int yhi, b200fdtd_session** session);
+int b200fdtd_session_set_peers(b200fdtd_session* session, void* workspace_low_neighbour,
+                               void* workspace_high_neighbour);
+int b200fdtd_session_slab_reset(b200fdtd_session* session, void* stream);
+
+/* Peer-mappable device memory for slab workspaces: cudaMalloc + CUDA IPC.  _export writes the
+ * 64-byte IPC handle of an allocation made by _alloc; _open maps another process's handle on the
+ * current device (enabling peer access); _close unmaps; _free releases. */
+int b200fdtd_peer_alloc(size_t bytes, void** ptr);
+int b200fdtd_peer_free(void* ptr);
+int b200fdtd_peer_export(void* ptr, unsigned char handle[64]);
+int b200fdtd_peer_open(const unsigned char handle[64], void** ptr);
+int b200fdtd_peer_close(void* ptr);
 
 void b200fdtd_session_destroy(b200fdtd_session* session);
 

@@ -123,7 +123,8 @@ class CudaSlab:
     self.device = torch.device(device)
     names = ("epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa",
              "pml_sigma", "pml_alpha")
-    self.inputs = [torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
+    self.inputs = [loc[k].to(self.device, torch.float32).contiguous() if isinstance(loc[k], torch.Tensor)
+                   else torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
                    for k in names]
     L.b200fdtd_session_workspace_bytes.restype = ctypes.c_size_t
     nbytes = L.b200fdtd_session_workspace_bytes(ctypes.byref(self.d))
@@ -408,7 +409,8 @@ class CudaSlabY:
     self.device = torch.device(device)
     names = ("epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa",
              "pml_sigma", "pml_alpha")
-    self.inputs = [torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
+    self.inputs = [loc[k].to(self.device, torch.float32).contiguous() if isinstance(loc[k], torch.Tensor)
+                   else torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
                    for k in names]
     L.b200fdtd_session_workspace_bytes.restype = ctypes.c_size_t
     nbytes = L.b200fdtd_session_workspace_bytes(ctypes.byref(self.d))
@@ -499,12 +501,13 @@ class YSlabRun:
   """One y-decomposed engine call: set-up in ``__init__``, the time loop in ``run``."""
 
   def __init__(self, kw, ghost=8, group=None, make_slab=None, device=None, kernel="auto",
-               local=None):
+               local=None, solo=False):
     """``local`` = a pre-built ``(local kwargs, nloc, crop)`` triple (what ``local_problem_y``
-    returns) for domains whose global arrays are too large to materialise on every rank."""
+    returns) for domains whose global arrays are too large to materialise on every rank.
+    ``solo``: wrap the slab onto itself on this rank alone, whatever process group exists."""
     self.kw, self.group = kw, group
     self.world, self.rank = 1, 0
-    if dist.is_available() and dist.is_initialized():
+    if not solo and dist.is_available() and dist.is_initialized():
       self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
     self.G = choose_ghost(kw, self.world) if ghost is None else int(ghost)
     loc, self.nloc, self.crop = (local if local is not None else
@@ -581,4 +584,213 @@ def fdtdz_decomposed_y(epsilon, dt, source_field, source_waveform, source_positi
   out = run.gathered_snapshots() if gather else run.local_snapshots()
   if gather:
     run.close()
+  return out
+
+
+# ===================================================================================================
+# y-slab decomposition with IN-KERNEL halo exchange: peer-mapped stores over NVLink, one launch
+# ===================================================================================================
+#
+# The ghost-zone scheme above pays (Yo + 2G) / Yo redundant work, one host-driven NCCL round per G
+# steps and a pipeline fill/drain per launch.  Here every rank keeps ONE ghost column per side and
+# the persistent kernel itself does the exchange (include/b200fdtd.h, "y-slab sessions"): the warp
+# that owns a slab's edge column stores its new fields into the neighbour's ghost column through
+# peer-mapped memory, the edge tile's progress counter goes into the neighbour's mirror slot, and
+# the neighbour's edge tiles wait on it like on any local tile.  The whole run is one launch per
+# GPU; transfers overlap the interior update tile by tile; no redundant cells.  Bit-identical to the
+# single-GPU run by construction (every owned cell sees the same operands in the same order).
+
+
+class CudaSlabP2P:
+  """y-slab engine over ``b200fdtd_session_create_slab`` + peer-mapped workspaces."""
+
+  def __init__(self, loc, device, group=None, solo=False):
+    """``solo``: the slab's neighbours are the slab itself on this rank alone (no collectives),
+    whatever process group exists -- the 1-GPU reference of a weak-scaling measurement."""
+    from . import fdtdz_jax as shim
+    self.shim, self.group = shim, group
+    L = self.L = shim.lib()
+    self.world, self.rank = 1, 0
+    if not solo and dist.is_available() and dist.is_initialized():
+      self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    loc = dict(loc)
+    lp = dict(loc.get("launch_params") or {})
+    lp["kernel"] = "systolic_lean"
+    loc["launch_params"] = lp
+    self.d = shim.make_desc(**{k: loc[k] for k in (
+        "epsilon", "dt", "source_field", "source_waveform", "source_position", "absorption_mask",
+        "pml_kappa", "pml_sigma", "pml_alpha", "pml_widths", "output_steps",
+        "use_reduced_precision", "launch_params", "offset")})
+    self.device = torch.device(device)
+    names = ("epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa",
+             "pml_sigma", "pml_alpha")
+    self.inputs = [loc[k].to(self.device, torch.float32).contiguous() if isinstance(loc[k], torch.Tensor)
+                   else torch.from_numpy(np.ascontiguousarray(_np(loc[k]), np.float32)).to(self.device)
+                   for k in names]
+    Y = self.d.Y
+    L.b200fdtd_session_workspace_bytes_slab.restype = ctypes.c_size_t
+    L.b200fdtd_session_workspace_bytes_slab.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    nbytes = L.b200fdtd_session_workspace_bytes_slab(ctypes.byref(self.d), 1, Y - 1)
+    if nbytes == 0:
+      raise RuntimeError(shim._last_error())
+    self.nbytes = nbytes
+    L.b200fdtd_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.c_void_p]
+    L.b200fdtd_peer_free.argtypes = [ctypes.c_void_p]
+    L.b200fdtd_peer_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.b200fdtd_peer_open.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.b200fdtd_peer_close.argtypes = [ctypes.c_void_p]
+    self.ws = ctypes.c_void_p()
+    self._opened = []
+    with torch.cuda.device(self.device):
+      self._check(L.b200fdtd_peer_alloc(nbytes, ctypes.byref(self.ws)))
+      nout = L.b200fdtd_num_outputs(ctypes.byref(self.d))
+      self.out = torch.zeros((nout, 3, self.d.xx, self.d.yy, self.d.zz), dtype=torch.float32,
+                             device=self.device)
+      self.session = ctypes.c_void_p()
+      L.b200fdtd_session_create_slab.argtypes = [
+          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+      self._check(L.b200fdtd_session_create_slab(
+          ctypes.byref(self.d), shim._void_array([t.data_ptr() for t in self.inputs]),
+          shim._void_array([self.out.data_ptr()]), self.ws, nbytes, self._stream(), 1, Y - 1,
+          ctypes.byref(self.session)))
+      lo, hi = self._map_neighbours()
+      L.b200fdtd_session_set_peers.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+      self._check(L.b200fdtd_session_set_peers(self.session, lo, hi))
+    L.b200fdtd_session_advance.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_void_p]
+    L.b200fdtd_session_slab_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.b200fdtd_session_destroy.argtypes = [ctypes.c_void_p]
+    L.b200fdtd_session_destroy.restype = None
+    info = (ctypes.c_int64 * 16)()
+    L.b200fdtd_session_layout2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.b200fdtd_session_layout2(self.session, info)
+    self.stages = int(info[15])
+    self.kernel = "systolic_lean"
+
+  def _check(self, rc):
+    if rc:
+      raise RuntimeError(self.shim._last_error())
+
+  def _stream(self):
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def _map_neighbours(self):
+    """Device addresses of the low / high neighbour's workspace in THIS process (CUDA IPC)."""
+    if self.world == 1:
+      return self.ws, self.ws                                # the slab wraps onto itself
+    # Every step below is collective-safe: a failure on one rank is agreed on by all of them
+    # before anybody raises, so that the caller can fall back to the NCCL path in step.
+    handle = (ctypes.c_ubyte * 64)()
+    ok = self.L.b200fdtd_peer_export(self.ws, handle) == 0
+    err = "" if ok else self.shim._last_error()
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+    allh = [torch.empty_like(mine) for _ in range(self.world)]
+    dist.all_gather(allh, mine, group=self.group)
+    shapes = torch.tensor([int(ok), self.nbytes, self.d.X, self.d.Y, self.d.Z], dtype=torch.int64,
+                          device=self.device)
+    alls = [torch.empty_like(shapes) for _ in range(self.world)]
+    dist.all_gather(alls, shapes, group=self.group)
+    if any(int(a[0]) == 0 for a in alls):
+      raise RuntimeError(f"CUDA IPC export failed on some rank: {err}")
+    if any(not torch.equal(a, shapes) for a in alls):
+      raise ValueError("in-kernel halo exchange needs the same local shape on every rank: "
+                       f"{[a.tolist() for a in alls]}")
+    ptrs = {self.rank: self.ws}
+    for r in {(self.rank - 1) % self.world, (self.rank + 1) % self.world} - {self.rank}:
+      hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+      p = ctypes.c_void_p()
+      if self.L.b200fdtd_peer_open(hb, ctypes.byref(p)) == 0:
+        self._opened.append(p)
+        ptrs[r] = p
+      else:
+        ok, err = False, self.shim._last_error()
+    flag = torch.tensor([int(ok)], device=self.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+    if int(flag.item()) == 0:
+      raise RuntimeError(f"CUDA IPC mapping of a neighbour's workspace failed on some rank: {err}")
+    return ptrs[(self.rank - 1) % self.world], ptrs[(self.rank + 1) % self.world]
+
+  def _barrier(self):
+    torch.cuda.synchronize(self.device)
+    if self.world > 1:
+      dist.barrier(group=self.group)
+
+  def advance(self, n0, nsteps):
+    self._barrier()                      # every rank has finished its previous launch
+    with torch.cuda.device(self.device):
+      self._check(self.L.b200fdtd_session_slab_reset(self.session, self._stream()))
+    self._barrier()                      # every rank's counters and mirror slots are clear
+    with torch.cuda.device(self.device):
+      self._check(self.L.b200fdtd_session_advance(self.session, int(n0), int(nsteps), self._stream()))
+
+  def snapshots(self):
+    return self.out
+
+  def close(self):
+    if getattr(self, "session", None):
+      self._barrier()                    # nobody is still storing into this workspace
+      self.L.b200fdtd_session_destroy(self.session)
+      self.session = ctypes.c_void_p()
+      for p in self._opened:
+        self.L.b200fdtd_peer_close(p)
+      self._opened = []
+      if self.world > 1:
+        dist.barrier(group=self.group)   # every mapping is closed before the memory goes away
+      self.L.b200fdtd_peer_free(self.ws)
+      self.ws = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      if getattr(self, "session", None) and self.world == 1:
+        self.close()
+    except Exception:
+      pass
+
+
+class P2PSlabRun:
+  """One y-decomposed engine call with in-kernel halo exchange: set-up in ``__init__``, the time
+  loop (ONE persistent launch per GPU) in ``run``.  Same interface as ``YSlabRun``."""
+
+  def __init__(self, kw, group=None, device=None, local=None, solo=False):
+    self.kw, self.group = kw, group
+    self.world, self.rank = 1, 0
+    if not solo and dist.is_available() and dist.is_initialized():
+      self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+    self.G = 1
+    loc, self.nloc, self.crop = (local if local is not None else
+                                 local_problem_y(kw, self.rank, self.world, 1))
+    if not torch.cuda.is_available():
+      raise RuntimeError("P2PSlabRun needs a CUDA device (no CPU fallback)")
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    self.slab = CudaSlabP2P(loc, dev, group, solo=solo)
+    self.tt = _np(loc["source_waveform"]).shape[0]
+
+  def run(self):
+    self.slab.advance(0, self.tt)
+
+  local_snapshots = YSlabRun.local_snapshots
+  gathered_snapshots = YSlabRun.gathered_snapshots
+
+  def close(self):
+    self.slab.close()
+
+
+def fdtdz_decomposed_p2p(epsilon, dt, source_field, source_waveform, source_position,
+                         absorption_mask, pml_kappa, pml_sigma, pml_alpha, pml_widths,
+                         output_steps, use_reduced_precision, launch_params=None, offset=(0, 0, 0),
+                         *, group=None, device=None, gather=True):
+  """The engine call, y-decomposed with in-kernel halo exchange over peer-mapped memory.  Same
+  contract as ``fdtdz_decomposed_y``; needs fp32 storage, 125 <= Z <= 128 and Y divisible by the
+  number of ranks."""
+  kw = dict(epsilon=epsilon, dt=dt, source_field=source_field, source_waveform=source_waveform,
+            source_position=source_position, absorption_mask=absorption_mask,
+            pml_kappa=pml_kappa, pml_sigma=pml_sigma, pml_alpha=pml_alpha,
+            pml_widths=pml_widths, output_steps=output_steps,
+            use_reduced_precision=use_reduced_precision, launch_params=launch_params,
+            offset=offset)
+  run = P2PSlabRun(kw, group=group, device=device)
+  run.run()
+  out = run.gathered_snapshots() if gather else run.local_snapshots()
+  run.close()
   return out

@@ -258,6 +258,10 @@ def project_snapshots(fields, omega, output_steps, dt):
   phases = _output_phases(omega, output_steps, dt)
   pinv = np.linalg.pinv(phases.T)                       # (2ww, n_out)
   fields = _as_tensor(fields, dtype=torch.float32)
+  if fields.is_cuda:
+    # one pass over the snapshots, complex phasors written interleaved (b200fdtd_project)
+    from . import fdtdz_jax
+    return fdtdz_jax.project(fields, pinv.astype(np.float32))
   w = torch.from_numpy(pinv.astype(np.float32)).to(fields.device)
   outputs = torch.einsum("ij,j...->i...", w, fields)
   return torch.complex(outputs[:ww], outputs[ww:])
@@ -325,6 +329,44 @@ def _overlap(mode, beta, pos, is_fwd, output):
   return _amplitudes(beta, vals, x)
 
 
+def _overlap_geometry(beta, pos, is_fwd):
+  """Sample planes, their offsets from the port and the signed beta of ``_overlap`` (:305-321)."""
+  beta = np.asarray(beta, np.float64).reshape(-1).copy()
+  if is_fwd is None:
+    return (pos, pos), np.array([0, 0]), beta * 0
+  if is_fwd:
+    return (pos + 1, pos + 2), np.array([1, 2]), beta
+  return (pos - 2, pos - 1), np.array([-2, -1]), -beta
+
+
+def _overlaps_fused(fields, modes, betas, pos, is_fwd):
+  """``amplitudes`` and ``svals`` of ``_scatter_impl`` with ALL nports^2 two-plane overlaps formed by
+  one kernel launch (``b200fdtd_overlaps``) instead of nports^2 x 2 eager slice-multiply-sum chains;
+  the 2x2 least-squares fits (``_amplitudes``) stay on the host-built pinv."""
+  from . import fdtdz_jax
+  dev = fields[0].device
+  geo = [_overlap_geometry(b, p, fwd) for b, p, fwd in zip(betas, pos, is_fwd)]
+  ms = [_as_tensor(m, dev) for m in modes]
+  axes = ["xyz".find(_prop_axis(m)) for m in ms]
+  flat = []
+  for m in ms:                                         # (ww|1, 2, xx|1, yy|1, zz|1) -> (ww, 2, U, V)
+    m = m.reshape((m.shape[0], 2) + tuple(d for d in m.shape[-3:] if d != 1)) \
+        if tuple(m.shape[-3:]).count(1) == 1 else m
+    flat.append(m)
+  vals = fdtdz_jax.overlaps(fields, flat, axes, [g[0] for g in geo])   # (F, M, 2, ww)
+  coefs = [[_amplitudes(g[2], vals[f, m].transpose(0, 1), g[1]) for m, g in enumerate(geo)]
+           for f in range(len(fields))]                                # each (ww, 2): in, out
+  amplitudes = []
+  for i, fwd in enumerate(is_fwd):
+    if fwd is None:
+      amplitudes.append(torch.ones(vals.shape[-1], dtype=torch.complex64, device=dev))
+    else:
+      amplitudes.append(coefs[i][i][:, 0])
+  svals = [[coefs[f][m][:, 1] / amplitudes[f] for m in range(len(modes))]
+           for f in range(len(fields))]
+  return amplitudes, svals
+
+
 def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=None,
                   group=None, want_grads=True, fuse_projection=False):
   """Mirror of ``_scatter_impl`` (:346-384).  One independent engine run per port; with a
@@ -358,16 +400,19 @@ def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=
   else:
     fields = [local[i] for i in range(nports)]
 
-  amplitudes = []
-  for f, m, b, p, fwd in zip(fields, modes, betas, pos, is_fwd):
-    if fwd is None:
-      amplitudes.append(torch.ones(np.asarray(b).reshape(-1).shape[0],
-                                   dtype=torch.complex64, device=f.device))
-    else:
-      amplitudes.append(_overlap(m, b, p, fwd, f)[:, 0])
-  svals = [[_overlap(m, b, p, fwd, f)[:, 1] / a
-            for m, b, p, fwd in zip(modes, betas, pos, is_fwd)]
-           for a, f in zip(amplitudes, fields)]
+  if fields[0].is_cuda and nports <= 16:
+    amplitudes, svals = _overlaps_fused(fields, modes, betas, pos, is_fwd)
+  else:
+    amplitudes = []
+    for f, m, b, p, fwd in zip(fields, modes, betas, pos, is_fwd):
+      if fwd is None:
+        amplitudes.append(torch.ones(np.asarray(b).reshape(-1).shape[0],
+                                     dtype=torch.complex64, device=f.device))
+      else:
+        amplitudes.append(_overlap(m, b, p, fwd, f)[:, 0])
+    svals = [[_overlap(m, b, p, fwd, f)[:, 1] / a
+              for m, b, p, fwd in zip(modes, betas, pos, is_fwd)]
+             for a, f in zip(amplitudes, fields)]
   grads = None
   if want_grads:
     grads = [[fi * fj / a[:, None, None, None, None] for fj in fields]

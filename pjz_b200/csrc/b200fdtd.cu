@@ -113,6 +113,7 @@ static Geom make_geom(const b200fdtd_desc* d) {
   g.n_out = num_outputs(d);
   g.tt = d->tt;
   g.n0 = 0;
+  g.ylo = 0; g.yhi = d->Y;
   g.dt = d->dt;
   g.P = (long long)g.Y * g.Zp;
   g.N = (long long)g.X * g.P;
@@ -237,6 +238,9 @@ static int make_plan_t(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
 }
 
 static int make_plan(const b200fdtd_desc* d, const Geom& g, Plan* plan) {
+  if (g.yhi - g.ylo != g.Y && (d->use_reduced_precision || g.Zq != 32))
+    return fail(B200FDTD_EUNSUPPORTED,
+                "y-slab sessions need the warp-per-column-pair kernel (fp32, 125 <= Z <= 128)");
   return d->use_reduced_precision ? make_plan_t<__half>(d, g, plan) : make_plan_t<float>(d, g, plan);
 }
 
@@ -734,6 +738,59 @@ int b200fdtd_adjoint_reduce(int nports, int ww, size_t nvox, const void* const* 
 }
 
 
+// ---- snapshot projection + port overlaps -------------------------------------
+
+int b200fdtd_project(int ww, int n_out, size_t nvox, const void* snapshots, const void* weights,
+                     void* out, void* stream) {
+  if (ww < 1 || n_out < 1) return fail(B200FDTD_EINVAL, "project: ww and n_out must be positive");
+  if (!snapshots || !weights || !out) return fail(B200FDTD_EINVAL, "project: NULL argument");
+  if (nvox == 0) return B200FDTD_OK;
+  int sms = 0, l2 = 0;
+  int rc = device_props(&sms, &l2);
+  if (rc) return rc;
+  const cudaError_t e = project_launch(static_cast<const float*>(snapshots),
+                                       static_cast<const float*>(weights), ww, n_out, nvox,
+                                       static_cast<float2*>(out), sms,
+                                       static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(B200FDTD_ECUDA, "project launch failed: %s", cudaGetErrorString(e));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_overlaps(int nfields, int nports, int ww, int xx, int yy, int zz,
+                      const void* const* fields, const void* const* modes, const int* axes,
+                      const int* planes, void* vals, void* stream) {
+  if (nfields < 1 || nfields > kOvlMaxPorts || nports < 1 || nports > kOvlMaxPorts)
+    return fail(B200FDTD_EINVAL, "overlaps: nfields and nports must be in [1, %d]", kOvlMaxPorts);
+  if (ww < 1 || xx < 1 || yy < 1 || zz < 1) return fail(B200FDTD_EINVAL, "overlaps: bad extents");
+  if (!fields || !modes || !axes || !planes || !vals)
+    return fail(B200FDTD_EINVAL, "overlaps: NULL argument");
+  OverlapFields f;
+  OverlapJobs j;
+  const int dims[3] = {xx, yy, zz};
+  for (int i = 0; i < kOvlMaxPorts; ++i) { f.f[i] = nullptr; j.j[i].mode = nullptr; }
+  for (int i = 0; i < nfields; ++i) {
+    if (!fields[i]) return fail(B200FDTD_EINVAL, "overlaps: fields[%d] is NULL", i);
+    f.f[i] = static_cast<const float2*>(fields[i]);
+  }
+  for (int m = 0; m < nports; ++m) {
+    if (!modes[m]) return fail(B200FDTD_EINVAL, "overlaps: modes[%d] is NULL", m);
+    if (axes[m] < 0 || axes[m] > 2) return fail(B200FDTD_EINVAL, "overlaps: axes[%d] must be 0..2", m);
+    for (int k = 0; k < 2; ++k)
+      if (planes[2 * m + k] < 0 || planes[2 * m + k] >= dims[axes[m]])
+        return fail(B200FDTD_EINVAL, "overlaps: sample plane %d of port %d outside [0,%d)",
+                    planes[2 * m + k], m, dims[axes[m]]);
+    j.j[m].mode = static_cast<const float2*>(modes[m]);
+    j.j[m].axis = axes[m];
+    j.j[m].plane[0] = planes[2 * m]; j.j[m].plane[1] = planes[2 * m + 1];
+  }
+  overlap_kernel<<<(unsigned)(nfields * nports * 2 * ww), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      f, j, nfields, nports, ww, xx, yy, zz, static_cast<float2*>(vals));
+  CUDA_TRY(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+
 // ---- waveguide-mode operator ------------------------------------------------------
 
 int b200fdtd_mode_operator(int ww, int uu, int vv, int mm, const void* eps, const void* omega,
@@ -841,6 +898,9 @@ struct b200fdtd_session {
   Ptrs<float> pf;
   Ptrs<__half> ph;
   dim3 grid;
+  bool slab;            // y-slab session: tiles cover [g.ylo, g.yhi), in-kernel halo exchange
+  bool peers_set;
+  SlabPeers peers;
 };
 
 // Sessions use the lean systolic kernels when the plan selects them (fp32 with 32 z-vectors, or
@@ -866,6 +926,27 @@ static int session_plan(const b200fdtd_desc* desc, const Geom& g, Plan* plan, bo
   return B200FDTD_OK;
 }
 
+static int slab_geom(const b200fdtd_desc* desc, int ylo, int yhi, Geom* g) {
+  *g = make_geom(desc);
+  if (ylo == 0 && yhi == desc->Y) return B200FDTD_OK;     // the whole domain: an ordinary session
+  if (ylo < 1 || yhi <= ylo || yhi > desc->Y - 1)
+    return fail(B200FDTD_EINVAL, "slab columns [%d,%d) need one ghost column on each side of Y=%d",
+                ylo, yhi, desc->Y);
+  g->ylo = ylo; g->yhi = yhi;
+  return B200FDTD_OK;
+}
+
+size_t b200fdtd_session_workspace_bytes_slab(const b200fdtd_desc* desc, int ylo, int yhi) {
+  if (validate(desc)) return 0;
+  Geom g;
+  if (slab_geom(desc, ylo, yhi, &g)) return 0;
+  Plan plan;
+  bool systolic;
+  if (session_plan(desc, g, &plan, &systolic)) return 0;
+  if (g.yhi - g.ylo != g.Y && !systolic) return 0;
+  return carve(g, desc->use_reduced_precision != 0, systolic, &plan.sys).total;
+}
+
 size_t b200fdtd_session_workspace_bytes(const b200fdtd_desc* desc) {
   if (validate(desc)) return 0;
   const Geom g = make_geom(desc);
@@ -878,6 +959,13 @@ size_t b200fdtd_session_workspace_bytes(const b200fdtd_desc* desc) {
 int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs,
                             void* const* outputs, void* workspace, size_t workspace_bytes,
                             void* stream, b200fdtd_session** session) {
+  return b200fdtd_session_create_slab(desc, inputs, outputs, workspace, workspace_bytes, stream,
+                                      0, desc ? desc->Y : 0, session);
+}
+
+int b200fdtd_session_create_slab(const b200fdtd_desc* desc, const void* const* inputs,
+                                 void* const* outputs, void* workspace, size_t workspace_bytes,
+                                 void* stream, int ylo, int yhi, b200fdtd_session** session) {
   int rc = validate(desc);
   if (rc) return rc;
   if (!session) return fail(B200FDTD_EINVAL, "session is NULL");
@@ -885,11 +973,17 @@ int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs
   for (int i = 0; i < B200FDTD_NUM_INPUTS; ++i)
     if (!inputs[i]) return fail(B200FDTD_EINVAL, "inputs[%d] is NULL", i);
   if (num_outputs(desc) > 0 && !outputs[0]) return fail(B200FDTD_EINVAL, "outputs[0] is NULL");
-  const Geom g = make_geom(desc);
+  Geom g;
+  rc = slab_geom(desc, ylo, yhi, &g);
+  if (rc) return rc;
+  const bool slab = g.yhi - g.ylo != g.Y;
   Plan plan;
   bool systolic;
   rc = session_plan(desc, g, &plan, &systolic);
   if (rc) return rc;
+  if (slab && !(systolic && plan.sys.cols == 2))
+    return fail(B200FDTD_EUNSUPPORTED,
+                "y-slab sessions need the warp-per-column-pair kernel (fp32, 125 <= Z <= 128)");
   if (!systolic && g.X > 65535) return fail(B200FDTD_EUNSUPPORTED, "per-step sessions support X <= 65535");
   const Workspace w = carve(g, desc->use_reduced_precision != 0, systolic, &plan.sys);
   if (workspace_bytes < w.total)
@@ -900,6 +994,8 @@ int b200fdtd_session_create(const b200fdtd_desc* desc, const void* const* inputs
   if (!s) return fail(B200FDTD_EINVAL, "out of host memory");
   s->d = *desc; s->g = g; s->w = w; s->ws = static_cast<char*>(workspace);
   s->plan = plan; s->systolic = systolic;
+  s->slab = slab; s->peers_set = false;
+  s->peers.delta_lo = 0; s->peers.delta_hi = 0; s->peers.enabled = slab ? 1 : 0;
   s->reduced = desc->use_reduced_precision != 0;
   s->grid = dim3((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads, g.X);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -951,16 +1047,40 @@ int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stre
   Geom g = s->g;
   g.n0 = n0;
   g.tt = n0 + nsteps;
-  CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
+  if (s->slab && !s->peers_set)
+    return fail(B200FDTD_EINVAL, "slab session: call b200fdtd_session_set_peers first");
+  // A slab's counters (and the mirror slots its neighbours write) are cleared by
+  // b200fdtd_session_slab_reset, between two barriers of the caller -- not here.
+  if (!s->slab)
+    CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
   unsigned* const sync = reinterpret_cast<unsigned*>(s->ws + s->w.sync);
   int rc;
   if (s->plan.sys.cols == 16)                      // sub-warp variant: fp16 or fp32 storage
     rc = s->reduced ? lean16_launch<__half>(g, s->ph, s->plan.sys, sync, st)
                     : lean16_launch<float>(g, s->pf, s->plan.sys, sync, st);
   else
-    rc = lean_launch(g, s->pf, s->plan.sys, sync, st);
+    rc = lean_launch(g, s->pf, s->plan.sys, sync, st, s->slab ? &s->peers : nullptr);
   if (rc != 0)
     return fail(B200FDTD_ECUDA, "systolic launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_set_peers(b200fdtd_session* s, void* workspace_lo, void* workspace_hi) {
+  if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (!s->slab) return fail(B200FDTD_EINVAL, "not a y-slab session");
+  if (!workspace_lo || !workspace_hi) return fail(B200FDTD_EINVAL, "peer workspace is NULL");
+  s->peers.delta_lo = static_cast<char*>(workspace_lo) - s->ws;
+  s->peers.delta_hi = static_cast<char*>(workspace_hi) - s->ws;
+  s->peers.enabled = 1;
+  s->peers_set = true;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_session_slab_reset(b200fdtd_session* s, void* stream) {
+  if (!s) return fail(B200FDTD_EINVAL, "session is NULL");
+  if (!s->slab) return fail(B200FDTD_EINVAL, "not a y-slab session");
+  CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys),
+                           static_cast<cudaStream_t>(stream)));
   return B200FDTD_OK;
 }
 
@@ -991,6 +1111,39 @@ int b200fdtd_session_layout2(const b200fdtd_session* s, int64_t* info) {
   info[13] = s->systolic ? 1 : 0;                 // 1: state of step n lives in set n & 1
   info[14] = s->plan.kernel;
   info[15] = s->systolic ? s->plan.sys.stages : 0;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return fail(B200FDTD_EINVAL, "peer_alloc: bad argument");
+  CUDA_TRY(cudaMalloc(ptr, bytes));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_free(void* ptr) {
+  CUDA_TRY(cudaFree(ptr));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_export(void* ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle) return fail(B200FDTD_EINVAL, "peer_export: NULL argument");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle, &h, sizeof h);
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_open(const unsigned char handle[64], void** ptr) {
+  if (!ptr || !handle) return fail(B200FDTD_EINVAL, "peer_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_close(void* ptr) {
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
   return B200FDTD_OK;
 }
 

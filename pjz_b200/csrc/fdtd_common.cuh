@@ -25,6 +25,8 @@ struct Geom {
   int proj_rows, n_out; // fused projection: rows of W (0 = plain snapshots), snapshots per run
   int tt;              // one past the last step of this launch
   int n0;              // first step of this launch (stepping sessions; 0 for a whole run)
+  int ylo, yhi;        // y-columns the tiles cover: [0, Y), or the owned range of a slab whose
+                       // ghost columns ylo-1 and yhi are filled by the neighbouring GPUs (lean kernel)
   float dt;
   long long P;         // elements per x-plane   = Y * Zp
   long long N;         // elements per component = X * P

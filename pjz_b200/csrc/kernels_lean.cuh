@@ -66,6 +66,35 @@ __device__ __forceinline__ void discard_l2_line(const void* p) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
 
+// ---- y-slab sessions: halo exchange from inside the kernel (peer-mapped stores over NVLink) -----
+// One GPU owns the columns [g.ylo, g.yhi) of its local array; columns ylo-1 and yhi are ghosts.
+// The neighbouring GPUs run the same kernel on the same local geometry and behave exactly like
+// the tiles t-1 / t+1 of the periodic single-GPU run: the warp that owns the slab's last column
+// stores its new (E, H, psiH) also into the HIGH neighbour's low ghost column, the warp that owns
+// the first column stores (Ex, Ez) into the LOW neighbour's high ghost column, and the service
+// warp of an edge tile publishes its progress counter also into the neighbour's mirror slot
+// (st.release.sys behind the warps' system-scope fences).  Consumers read ghost data and mirror
+// counters from their OWN memory, so the k+3 rule and the WAR argument of DESIGN.md 4.5 carry over
+// with "tile t-1 / t+1" = the neighbour's edge tile.  All workspaces have the same layout, so a
+// peer address is the local address plus one byte offset per side.
+struct SlabPeers {
+  long long delta_lo, delta_hi;    // neighbour's workspace base minus mine (bytes); 0 = myself
+  int enabled;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename P>
+__device__ __forceinline__ P* peer_ptr(P* local, long long delta) {
+  return reinterpret_cast<P*>(reinterpret_cast<char*>(local) + delta);
+}
+
 __device__ __forceinline__ void f4_to_arr(const float4 r, float (&v)[4]) {
   v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
 }
@@ -73,11 +102,12 @@ __device__ __forceinline__ float4 arr_to_f4(const float (&v)[4]) {
   return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// U = unroll factor of the plane loop (2 removes the loop-carried register moves).
 // STATS = per-warp wait-time accounting printed at the end (debug builds of the plan only).
-template <int U, bool STATS>
+// SLAB = y-slab session: tiles cover [g.ylo, g.yhi), edge tiles exchange with the neighbour GPUs.
+template <bool STATS, bool SLAB>
 __global__ void __launch_bounds__(32 * (kLeanMaxWarps + 1), 1)
-lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync) {
+lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync,
+            const SlabPeers peers) {
   constexpr int VW = 4;
   constexpr int ZQ = 32;
   extern __shared__ float4 smem[];
@@ -87,8 +117,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
   const int S = cfg.stages, NT = cfg.ntiles;
   const int t = blockIdx.x % NT, j = blockIdx.x / NT;
-  const int y0 = (int)((long long)t * g.Y / NT);
-  const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
+  const int ybase = SLAB ? g.ylo : 0, yspan = SLAB ? g.yhi - g.ylo : g.Y;
+  const int y0 = ybase + (int)((long long)t * yspan / NT);
+  const int Yt = ybase + (int)((long long)(t + 1) * yspan / NT) - y0;
   const int X = g.X, Y = g.Y;
   const int psi_row = g.npg;                       // float4 per psi row of a slot
   const int eslot_f4 = kLeanERows * ZQ;
@@ -98,6 +129,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
 
   unsigned* const status = sync + (size_t)S * NT * kSysFlagStride;
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
+  unsigned* const mirror_lo = status + kSysFlagStride;            // [S]: low neighbour's last tile
+  unsigned* const mirror_hi = mirror_lo + (size_t)S * kSysFlagStride;   // high neighbour's first tile
+  const bool edge_lo = SLAB && t == 0, edge_hi = SLAB && t == NT - 1;
 
   if (tid < (int)(sizeof(LeanCtl) / sizeof(unsigned))) reinterpret_cast<unsigned*>(&ctl)[tid] = 0u;
   __syncthreads();
@@ -109,8 +143,15 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     const int jp = (j + S - 1) % S, jn = (j + 1) % S;
     const unsigned* watch = sync + ((size_t)jp * NT + wrapi(t - 1 + (lane < 3 ? lane : 1), NT)) *
                                        kSysFlagStride;
+    if constexpr (SLAB) {                          // beyond the slab: the neighbour GPU's edge tile
+      if (lane == 0 && t == 0) watch = mirror_lo + (size_t)jp * kSysFlagStride;
+      if (lane == 2 && t == NT - 1) watch = mirror_hi + (size_t)jp * kSysFlagStride;
+    }
     if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
     if (lane == 4) watch = status;
+    // my counter as the neighbours see it: their mirror slots (same layout, their workspace)
+    unsigned* const push_lo = peer_ptr(mirror_hi + (size_t)j * kSysFlagStride, peers.delta_lo);
+    unsigned* const push_hi = peer_ptr(mirror_lo + (size_t)j * kSysFlagStride, peers.delta_hi);
     // L2 prefetch duty: lanes 8..16 own one array each (E0..2, H0..2 of the read set, B0..2).
     const int ylo = max(y0 - 1, 0), yhi = min(y0 + Yt, Y - 1);
     const unsigned pf_bytes = (unsigned)((yhi - ylo + 1) * g.Zp * (int)sizeof(float));
@@ -124,13 +165,19 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dn = min(dn, __shfl_xor_sync(0xffffffffu, dn, o));
       if (dn != published) {
-        if (lane == 0) st_release_u32(my_prog, dn);
+        if (lane == 0) {
+          st_release_u32(my_prog, dn);
+          if constexpr (SLAB) {
+            if (edge_lo) st_release_sys_u32(push_lo, dn);
+            if (edge_hi) st_release_sys_u32(push_hi, dn);
+          }
+        }
         published = dn;
       } else if (ex == (unsigned)NW) {
         break;
       }
       unsigned v = 0xffffffffu;
-      if (lane < 5) v = ld_relaxed_gpu_u32(watch);
+      if (lane < 5) v = SLAB ? ld_relaxed_sys_u32(watch) : ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
                      v4 = __shfl_sync(0xffffffffu, v, 4);
@@ -192,6 +239,13 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const unsigned pvB = (unsigned)yB * g.npg + (has_psi ? slot : 0);
   const bool top = q + 1 == ZQ, bottom = q == 0;
   const bool discA = cA >= 2 && cA <= Yt - 1, discB = cB >= 2 && cB <= Yt - 1;
+  // slab edges: the first owned column is column B of warp 0 in tile 0; the last owned column is
+  // tile-local column Yt of the last tile
+  const bool push_lo_B = edge_lo && w == 0 && doHB;
+  const bool push_hi_A = edge_hi && cA == Yt && ownA, push_hi_B = edge_hi && cB == Yt;
+  const unsigned gv_lo = (unsigned)g.yhi * ZQ + q;               // neighbour's HIGH ghost column
+  const unsigned gv_hi = (unsigned)(SLAB ? g.ylo - 1 : 0) * ZQ + q;   // neighbour's LOW ghost column
+  const unsigned gp_hi = (unsigned)(SLAB ? g.ylo - 1 : 0) * g.npg + (has_psi ? slot : 0);
 
   float4* const wbase = smem + (size_t)w * warp_f4;
   float4* const hbase = wbase + 3 * eslot_f4;
@@ -398,7 +452,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
 #pragma unroll
     for (int v = 0; v < VW; ++v) { hypA[v] = 0.f; hzpA[v] = 0.f; hypB[v] = 0.f; hzpB[v] = 0.f; }
 
-#pragma unroll U
+#pragma unroll 1
     for (int i = 0; i <= X && ok; ++i) {
       const bool real = i >= 1;
       const int Pn = P + 1 == X ? 0 : P + 1;
@@ -555,6 +609,20 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvA), arr_to_f4(psxA)); __stcg(wPy + (pP + pvA), arr_to_f4(psyA));
             __stcg(ePx + (pP + pvA), arr_to_f4(qsx)); __stcg(ePy + (pP + pvA), arr_to_f4(qsy));
           }
+          if constexpr (SLAB) {
+            if (push_hi_A) {                         // -> the high neighbour's low ghost column
+              const unsigned og = vP + gv_hi;
+              const long long dl = peers.delta_hi;
+              __stcg(peer_ptr(wHx + og, dl), arr_to_f4(hxA)); __stcg(peer_ptr(wHy + og, dl), arr_to_f4(hyA));
+              __stcg(peer_ptr(wHz + og, dl), arr_to_f4(hzA));
+              __stcg(peer_ptr(wEx + og, dl), arr_to_f4(exA)); __stcg(peer_ptr(wEy + og, dl), arr_to_f4(eyA));
+              __stcg(peer_ptr(wEz + og, dl), arr_to_f4(ezA));
+              if (has_psi) {
+                __stcg(peer_ptr(wPx + (pP + gp_hi), dl), arr_to_f4(psxA));
+                __stcg(peer_ptr(wPy + (pP + gp_hi), dl), arr_to_f4(psyA));
+              }
+            }
+          }
           if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yA, q, exA, eyA, ezA, p.proj);
         }
         if (doHB) {
@@ -582,12 +650,32 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvB), arr_to_f4(psxB)); __stcg(wPy + (pP + pvB), arr_to_f4(psyB));
             __stcg(ePx + (pP + pvB), arr_to_f4(qsx)); __stcg(ePy + (pP + pvB), arr_to_f4(qsy));
           }
+          if constexpr (SLAB) {
+            if (push_hi_B) {                         // -> the high neighbour's low ghost column
+              const unsigned og = vP + gv_hi;
+              const long long dl = peers.delta_hi;
+              __stcg(peer_ptr(wHx + og, dl), arr_to_f4(hxB)); __stcg(peer_ptr(wHy + og, dl), arr_to_f4(hyB));
+              __stcg(peer_ptr(wHz + og, dl), arr_to_f4(hzB));
+              __stcg(peer_ptr(wEx + og, dl), arr_to_f4(exB)); __stcg(peer_ptr(wEy + og, dl), arr_to_f4(eyB));
+              __stcg(peer_ptr(wEz + og, dl), arr_to_f4(ezB));
+              if (has_psi) {
+                __stcg(peer_ptr(wPx + (pP + gp_hi), dl), arr_to_f4(psxB));
+                __stcg(peer_ptr(wPy + (pP + gp_hi), dl), arr_to_f4(psyB));
+              }
+            }
+            if (push_lo_B) {                         // -> the low neighbour's high ghost column
+              const unsigned og = vP + gv_lo;
+              __stcg(peer_ptr(wEx + og, peers.delta_lo), arr_to_f4(exB));
+              __stcg(peer_ptr(wEz + og, peers.delta_lo), arr_to_f4(ezB));
+            }
+          }
           if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yB, q, exB, eyB, ezB, p.proj);
         }
         // every store of sweep indices <= i has been issued by this warp
         __syncwarp();
         if (lane == 0) {
-          __threadfence_block();
+          if (SLAB && (edge_lo || edge_hi)) __threadfence_system();   // peer stores before the counter
+          else __threadfence_block();
           st_vol_s(&ctl.wdone[w], base_mine + (unsigned)i);
         }
       } else if (w > 0 && lane == 0) {
@@ -616,9 +704,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
 }
 
-inline const void* lean_fn(int unroll, bool stats) {
-  if (stats) return (const void*)lean_kernel<1, true>;
-  return unroll == 2 ? (const void*)lean_kernel<2, false> : (const void*)lean_kernel<1, false>;
+inline const void* lean_fn(bool stats, bool slab) {
+  if (slab) return (const void*)lean_kernel<false, true>;
+  return stats ? (const void*)lean_kernel<true, false> : (const void*)lean_kernel<false, false>;
 }
 
 // Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.
@@ -640,9 +728,11 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   while (max_tile >= 1 && lean_smem_bytes(g, max_tile) + 256 > 227 * 1024) --max_tile;
   if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
-  if (max_tile > g.Y) max_tile = g.Y;
-  const int ntiles = (g.Y + max_tile - 1) / max_tile;
-  const int widest = (g.Y + ntiles - 1) / ntiles;
+  const int Yspan = g.yhi - g.ylo;               // the whole domain, or a slab's owned columns
+  if (Yspan < 1) { *why = "empty column range"; return false; }
+  if (max_tile > Yspan) max_tile = Yspan;
+  const int ntiles = (Yspan + max_tile - 1) / max_tile;
+  const int widest = (Yspan + ntiles - 1) / ntiles;
   cfg->tile_y = widest;
   cfg->ntiles = ntiles;
   cfg->cols = 2;
@@ -664,8 +754,8 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   int occ = 0;
   cfg->need_zfix = 0;
   cfg->unroll = 1;
-  if (const char* e = getenv("B200FDTD_LEAN_UNROLL")) cfg->unroll = atoi(e) == 2 ? 2 : 1;
-  const void* fn = lean_fn(cfg->unroll, getenv("B200FDTD_LEAN_STATS") != nullptr);
+  const bool slab = Yspan != g.Y;
+  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -691,15 +781,19 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
 }
 
 inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& cfg, unsigned* sync,
-                       cudaStream_t st) {
-  const void* fn = lean_fn(cfg.unroll, getenv("B200FDTD_LEAN_STATS") != nullptr);
+                       cudaStream_t st, const SlabPeers* peers = nullptr) {
+  const bool slab = peers != nullptr && peers->enabled;
+  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;
   Geom gg = g;
   Ptrs<float> pp = p;
   SystolicCfg cc = cfg;
-  void* args[] = {&gg, &pp, &cc, &sync};
+  SlabPeers sp;
+  sp.delta_lo = 0; sp.delta_hi = 0; sp.enabled = 0;
+  if (slab) sp = *peers;
+  void* args[] = {&gg, &pp, &cc, &sync, &sp};
   e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles), dim3(cfg.threads), args,
                                   cfg.smem_bytes, st);
   if (e != cudaSuccess) return (int)e;

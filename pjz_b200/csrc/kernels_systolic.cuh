@@ -87,8 +87,11 @@ __device__ __forceinline__ bool wait_ge(const unsigned* flag, unsigned need, uns
   }
 }
 
+// Progress counters [stages][ntiles], the status word, then 2 x stages MIRROR slots: in a y-slab
+// session the neighbouring GPUs store the counters of their edge tiles there (low neighbour's
+// last tile, then high neighbour's first tile) -- see kernels_lean.cuh, SlabPeers.
 inline size_t systolic_sync_bytes(const SystolicCfg& c) {
-  return ((size_t)c.stages * c.ntiles + 1) * kSysFlagStride * sizeof(unsigned);
+  return ((size_t)c.stages * c.ntiles + 1 + 2 * (size_t)c.stages) * kSysFlagStride * sizeof(unsigned);
 }
 
 template <typename T>

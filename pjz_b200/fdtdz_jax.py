@@ -262,6 +262,69 @@ def adjoint_reduce(fields, coef):
   return out
 
 
+def project(snapshots, weights):
+  """Phasors from snapshots in one pass (``b200fdtd_project``): ``snapshots`` CUDA float32
+  ``(n_out, ...)``, ``weights`` ``(2*ww, n_out)`` = the pseudo-inverse of the sampled phases
+  (/root/reference/src/pjz/_field.py:272-279).  Returns complex64 ``(ww, ...)``."""
+  import torch
+  if not (_is_torch(snapshots) and snapshots.is_cuda):
+    raise RuntimeError("project needs a CUDA tensor (no CPU fallback)")
+  dev = snapshots.device
+  x = snapshots.to(torch.float32).contiguous()
+  w = torch.as_tensor(np.ascontiguousarray(np.asarray(weights, np.float32))).to(dev)
+  n_out = int(x.shape[0])
+  if w.ndim != 2 or w.shape[1] != n_out or w.shape[0] % 2:
+    raise ValueError(f"weights must have shape (2*ww, {n_out}), got {tuple(w.shape)}")
+  ww = int(w.shape[0]) // 2
+  nvox = int(x[0].numel())
+  out = torch.empty((ww,) + tuple(x.shape[1:]), dtype=torch.complex64, device=dev)
+  L = lib()
+  L.b200fdtd_project.restype = ctypes.c_int
+  L.b200fdtd_project.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+  with torch.cuda.device(dev):
+    rc = L.b200fdtd_project(ww, n_out, nvox, x.data_ptr(), w.data_ptr(), out.data_ptr(),
+                            torch.cuda.current_stream(dev).cuda_stream)
+  if rc != 0:
+    raise RuntimeError(f"b200fdtd_project failed ({rc}): {_last_error()}")
+  return out
+
+
+def overlaps(fields, modes, axes, planes):
+  """All two-plane mode overlaps at once (``b200fdtd_overlaps``,
+  /root/reference/src/pjz/_field.py:305-338).  ``fields``: F CUDA complex64 tensors
+  ``(ww, 3, xx, yy, zz)``; ``modes``: M tensors ``(ww, 2, ., ., .)`` with a singleton along the
+  port's axis; ``axes``: M ints; ``planes``: ``(M, 2)`` sample planes.  Returns complex64
+  ``(F, M, 2, ww)``: ``vals[f, m, k, w] = sum(mode_m[w] * transverse(fields_f[w]) at plane k)``."""
+  import torch
+  f0 = fields[0]
+  if not (_is_torch(f0) and f0.is_cuda):
+    raise RuntimeError("overlaps needs CUDA tensors (no CPU fallback)")
+  dev = f0.device
+  fs = [f.to(torch.complex64).contiguous() for f in fields]
+  ww, _, xx, yy, zz = (int(v) for v in f0.shape)
+  ms = []
+  for m in modes:
+    m = torch.as_tensor(m).to(dev)
+    if m.shape[0] != ww:
+      m = m.expand((ww,) + tuple(m.shape[1:]))
+    ms.append(m.to(torch.complex64).contiguous())
+  nf, nm = len(fs), len(ms)
+  ax = (ctypes.c_int * nm)(*[int(a) for a in axes])
+  pl = (ctypes.c_int * (2 * nm))(*[int(p) for row in planes for p in row])
+  vals = torch.empty((nf, nm, 2, ww), dtype=torch.complex64, device=dev)
+  L = lib()
+  L.b200fdtd_overlaps.restype = ctypes.c_int
+  L.b200fdtd_overlaps.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 6
+  with torch.cuda.device(dev):
+    rc = L.b200fdtd_overlaps(nf, nm, ww, xx, yy, zz, _void_array([f.data_ptr() for f in fs]),
+                             _void_array([m.data_ptr() for m in ms]), ax, pl, vals.data_ptr(),
+                             torch.cuda.current_stream(dev).cuda_stream)
+  if rc != 0:
+    raise RuntimeError(f"b200fdtd_overlaps failed ({rc}): {_last_error()}")
+  return vals
+
+
 def plan_info(**kwargs):
   """What the engine would launch for these arguments (kernel, tiling, CTAs ...)."""
   d = make_desc(**kwargs)

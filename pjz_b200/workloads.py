@@ -153,6 +153,43 @@ def metalens(total=(4096, 4096, 128), pad=32, pml=(16, 16), pitch=16, height=24,
   return eps, ports, params, np.array([OMEGA0])
 
 
+def metalens_columns(total, ycols, device, pad=32, pml=(16, 16), pitch=16, height=24, seed=1):
+  """The permittivity of ``metalens(total, ...)`` restricted to the user-domain columns ``ycols``
+  (clipped indices, i.e. edge replication already applied), built with torch on ``device``: one
+  rank of the decomposed cfg5 run builds only ITS slab -- the 4096x4096x128 stack (18 GB of
+  float32) is never materialised.  Same pillar lattice, radii and layers as ``metalens``."""
+  import torch
+  X, Y, Z = total
+  xx, yy, zz = X - 2 * pad, Y - 2 * pad, Z - sum(pml)
+  rng = np.random.default_rng(seed)
+  radii = torch.from_numpy(
+      rng.uniform(2, 7, (xx // pitch + 1, yy // pitch + 1)).astype(np.float32)).to(device)
+  zsub = zz // 3
+  yc = torch.as_tensor(np.asarray(ycols), dtype=torch.float32, device=device)
+  xs = torch.arange(xx, dtype=torch.float32, device=device)
+  eps = torch.empty((3, xx, yc.numel(), zz), dtype=torch.float32, device=device)
+  shifts = ((0.5, 0, 0), (0, 0.5, 0), (0, 0, 0.5))
+  for c, (sx, sy, sz) in enumerate(shifts):
+    x, y = (xs + sx)[:, None], (yc + sy)[None, :]
+    ix = torch.floor(x / pitch).long().clamp(0, radii.shape[0] - 1)
+    iy = torch.floor(y / pitch).long().clamp(0, radii.shape[1] - 1)
+    cx, cy = (ix + 0.5) * pitch, (iy + 0.5) * pitch
+    inside = ((x - cx) ** 2 + (y - cy) ** 2 < radii[ix, iy] ** 2)          # (xx, ny)
+    z = torch.arange(zz, dtype=torch.float32, device=device) + sz
+    layer = ((z >= zsub) & (z < zsub + height))[None, None, :]
+    pillar = inside[:, :, None] & layer
+    # metalens(): substrate below zsub, pillars or air in the layer, air above -- indexed by the
+    # INTEGER z plane (the reference builder overwrites whole planes after sampling)
+    zi = torch.arange(zz, device=device)
+    below = (zi < zsub)[None, None, :]
+    in_layer = ((zi >= zsub) & (zi < zsub + height))[None, None, :]
+    val = torch.where(below, torch.tensor(EPS_CLAD, device=device),
+                      torch.where(in_layer & pillar, torch.tensor(EPS_SI, device=device),
+                                  torch.tensor(1.0, device=device)))
+    eps[c] = val
+  return eps
+
+
 def port_mode(eps, axis, pos, omega, num_modes=1):
   """Mode of the cross-section of ``eps`` at the port plane (harness: pjz_b200.mode)."""
   from ._mode import mode

@@ -348,3 +348,90 @@ def test_two_gpu_decomposition_is_bit_exact(built, tmp_path):
   kw = random_problem(domain=(40, 24, 32), axis=0, pml=(4, 6), tt=40, seed=77,
                       output_steps=(20, 40, 6), src_pos=20)
   np.testing.assert_array_equal(np.load(out), fdtd_c.fdtdz(**kw))
+
+
+# ---- in-kernel halo exchange (peer-mapped stores, one launch per GPU) ---------------------------------
+
+P2P_CASES = [
+    # domain, pml, axis, src_pos, steps
+    ((10, 1, 128), (16, 16), 0, 4, 27),      # one owned column: the edge column is first AND last
+    ((9, 2, 128), (4, 6), 2, 20, 27),
+    ((9, 14, 125), (3, 5), 0, 3, 27),        # even tile width: the last owned column is a column A
+    ((11, 15, 128), (16, 16), 1, 7, 45),     # one full tile (odd width: last owned column is a B)
+    ((12, 16, 128), (16, 16), 2, 40, 33),    # two tiles
+    ((8, 47, 126), (0, 0), 1, 46, 27),       # y source on the last column: its partner is column 45
+    ((16, 64, 128), (16, 16), 0, 5, 64),     # several tiles and pipeline rounds
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("domain,pml,axis,src_pos,tt", P2P_CASES)
+def test_p2p_slab_wrapping_onto_itself_equals_one_call_engine(built, domain, pml, axis, src_pos, tt):
+  """World 1: the slab's low and high neighbour are the slab itself, so the edge warps store into
+  the slab's OWN ghost columns and the edge tiles watch their own mirror slots -- the same code
+  path as between two GPUs, minus NVLink.  Must reproduce the periodic one-call engine bit for
+  bit (and therefore the C oracle)."""
+  from oracle import fdtd_c
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import fdtdz_decomposed_p2p
+  from tests.problems import random_problem
+  kw = random_problem(domain=domain, axis=axis, pml=pml, tt=tt, seed=90 + axis, src_pos=src_pos,
+                      output_steps=(tt // 3, tt, 5), absorb_pad=min(3, domain[1] // 2))
+  got = fdtdz_decomposed_p2p(**kw).cpu().numpy()
+  np.testing.assert_array_equal(got, fdtd_c.fdtdz(**kw))
+  dev = dict(kw)
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  np.testing.assert_array_equal(got, fdtdz_jax.fdtdz(**dev).cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_p2p_slab_tilings_and_long_run(built):
+  """Explicit tilings (tile width / stage count through launch_params) and a longer run on a
+  wider slab: every plan gives the bits of the one-call engine."""
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import fdtdz_decomposed_p2p
+  from tests.problems import random_problem
+  kw = random_problem(domain=(24, 96, 128), axis=2, pml=(16, 16), tt=150, seed=5,
+                      output_steps=(60, 150, 41), absorb_pad=8, absorb_coeff=1e-3)
+  dev = dict(kw)
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  want = fdtdz_jax.fdtdz(**dev).cpu().numpy()
+  for lp in (None, {"tile_y": 5, "stages": 3}, {"tile_y": 13, "stages": 2}, {"tile_y": 1, "stages": 1}):
+    got = fdtdz_decomposed_p2p(**{**kw, "launch_params": lp}).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def _gpu_worker_p2p(rank, world, port, out_path):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  from pjz_b200._decomp import fdtdz_decomposed_p2p
+  from tests.problems import random_problem
+  outs = []
+  for axis, src_pos in ((1, 31), (1, 32), (0, 7), (2, 50)):   # y sources next to / on the cut
+    kw = random_problem(domain=(24, 64, 128), axis=axis, pml=(16, 16), tt=80, seed=78 + axis,
+                        output_steps=(20, 80, 12), src_pos=src_pos)
+    outs.append(fdtdz_decomposed_p2p(**kw).cpu().numpy())
+  if rank == 0:
+    np.savez(out_path, *outs)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_p2p_decomposition_is_bit_exact(built, tmp_path):
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs")
+  from oracle import fdtd_c
+  from tests.problems import random_problem
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "p2p.npz")
+  mp.spawn(_gpu_worker_p2p, args=(2, port, out), nprocs=2, join=True)
+  got = np.load(out)
+  for i, (axis, src_pos) in enumerate(((1, 31), (1, 32), (0, 7), (2, 50))):
+    kw = random_problem(domain=(24, 64, 128), axis=axis, pml=(16, 16), tt=80, seed=78 + axis,
+                        output_steps=(20, 80, 12), src_pos=src_pos)
+    np.testing.assert_array_equal(got[f"arr_{i}"], fdtd_c.fdtdz(**kw))

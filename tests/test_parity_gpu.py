@@ -506,3 +506,58 @@ def test_lean_long_run_matches_independent_kernel_at_baseline_size():
   assert fdtdz_jax.plan_info(**{**kw, "launch_params": None})["kernel"] == "systolic_lean"
   np.testing.assert_array_equal(a, b)
   assert np.isfinite(a).all() and np.abs(a[-1]).max() > 0
+
+
+# ---- one-pass snapshot projection and fused port overlaps ---------------------
+
+@pytest.mark.parametrize("ww,shape", [(1, (3, 8, 6, 4)), (2, (3, 9, 7, 5)), (4, (3, 40, 30, 20)),
+                                      (8, (3, 12, 10, 8)), (11, (3, 6, 5, 4)), (3, (3, 5, 3, 3))])
+def test_project_kernel_matches_the_reference_einsum(ww, shape):
+  """b200fdtd_project vs `einsum("ij,j...->i...", pinv, snapshots)` + complex()
+  (/root/reference/src/pjz/_field.py:272-279): <= 1e-6 of the largest phasor."""
+  g = torch.Generator().manual_seed(ww)
+  n_out = 2 * ww + 1
+  snaps = torch.randn((n_out,) + shape, generator=g)
+  W = torch.randn((2 * ww, n_out), generator=g)
+  want = torch.einsum("ij,j...->i...", W.double(), snaps.double())
+  want = torch.complex(want[:ww], want[ww:])
+  got = fdtdz_jax.project(snaps.cuda(), W.numpy())
+  assert got.shape == want.shape and got.dtype == torch.complex64
+  assert float((got.cpu() - want).abs().max()) <= 1e-6 * float(want.abs().max()) * n_out
+
+
+def test_project_snapshots_uses_the_kernel_on_cuda_and_agrees_with_the_cpu_path():
+  from pjz_b200 import _field as glue
+  omega = np.array([2 * np.pi / 37, 2 * np.pi / 33, 2 * np.pi / 41])
+  steps = (100, 100 + 7 * 9, 9)
+  snaps = torch.randn((7, 3, 10, 12, 8), generator=torch.Generator().manual_seed(3))
+  cpu = glue.project_snapshots(snaps, omega, steps, 0.5)
+  gpu = glue.project_snapshots(snaps.cuda(), omega, steps, 0.5)
+  assert gpu.is_cuda and gpu.dtype == torch.complex64
+  torch.testing.assert_close(gpu.cpu(), cpu, rtol=1e-5, atol=1e-6 * float(cpu.abs().max()))
+
+
+@pytest.mark.parametrize("nports", [1, 2, 3])
+def test_fused_overlaps_match_the_eager_formula(nports):
+  """b200fdtd_overlaps + host pinv vs the per-port slice-multiply-sum chains of `_overlap`
+  (/root/reference/src/pjz/_field.py:305-338) for x, y and z ports, forward / backward / None."""
+  from pjz_b200 import _field as glue
+  g = torch.Generator().manual_seed(10 + nports)
+  ww, xx, yy, zz = 2, 14, 12, 10
+  fields = [torch.complex(torch.randn((ww, 3, xx, yy, zz), generator=g),
+                          torch.randn((ww, 3, xx, yy, zz), generator=g)).cuda() for _ in range(nports)]
+  shapes = [(ww, 2, 1, yy, zz), (ww, 2, xx, 1, zz), (ww, 2, xx, yy, 1)]
+  modes = [torch.randn(shapes[i % 3], generator=g) for i in range(nports)]
+  if nports > 2:
+    modes[2] = torch.complex(modes[2], torch.randn(shapes[2], generator=g))
+  betas = [np.array([0.31 + 0.02 * i, 0.35]) for i in range(nports)]
+  pos = [4, 6, 5][:nports]
+  is_fwd = [True, False, None][:nports]
+  amps, svals = glue._overlaps_fused(fields, modes, betas, pos, is_fwd)
+  for i in range(nports):
+    want_a = (glue._overlap(modes[i], betas[i], pos[i], is_fwd[i], fields[i])[:, 0]
+              if is_fwd[i] is not None else torch.ones(ww, dtype=torch.complex64).cuda())
+    torch.testing.assert_close(amps[i], want_a, rtol=2e-5, atol=1e-5)
+    for j in range(nports):
+      want = glue._overlap(modes[j], betas[j], pos[j], is_fwd[j], fields[i])[:, 1] / want_a
+      torch.testing.assert_close(svals[i][j], want, rtol=2e-4, atol=1e-5 * float(want.abs().max() + 1))
