@@ -13,7 +13,8 @@ input construction (/root/reference/src/pjz/_field.py:171-279, 346-384).  The C 
   cfg3  512x512x128 demux: 60 steps at full size; the real 4-frequency ``output_steps`` schedule
         (9 snapshots, 246 steps apart, 1 969 steps minimum) on a 128x128x128 demux.
   cfg4  384x256x128 coupler, one x-port, 100 steps.
-  cfg5  a 64x4096x128 slab of the metalens (z-plane source), 30 steps.
+  cfg5  the metalens (z-plane source) at one rank's slab width (96x512x128, 40 steps) and 64 planes
+        of the full 4096-column width (30 steps).
   reduced precision at pjz's default geometry (fp16 storage, 96 z-cells, pml (16, 16)),
         2 400 steps: bit-exact against the C oracle's fp16-storage mode, and a MEASURED rel-L2
         against the fp32 run of the same inputs (9.0e-3 on the C oracle), asserted against the
@@ -216,13 +217,19 @@ def test_cfg4_coupler_one_port_is_bit_exact():
 
 
 def test_cfg5_metalens_slab_is_bit_exact():
-  """A 64-plane slab of the 4096x4096x128 metalens with its z-plane (quadrature) source: the
-  geometry one rank of the decomposed run sweeps."""
+  """The metalens with its z-plane (quadrature) source at the width ONE RANK of the decomposed
+  run sweeps (512 columns): the persistent kernel; and 64 planes of the full 4096-column width,
+  which no single-GPU persistent plan covers (274 y-tiles) -- AUTO must fall back and still give
+  the oracle's bits."""
+  eps, ports, params, omega = W.metalens(total=(96, 512, 128), pad=8)
+  kw = engine_kwargs(eps, ports, params, omega, port=0, tt=40, output_steps=(9, 40, 10))
+  assert kw["source_field"].shape == (2, 2, 96, 512, 1)
+  check_bit_exact(kw, "systolic_lean")
   eps, ports, params, omega = W.metalens(total=(64, 4096, 128), pad=8)
   kw = engine_kwargs(eps, ports, params, omega, port=0, tt=30, output_steps=(9, 30, 10))
   assert kw["source_field"].shape == (2, 2, 64, 4096, 1)
   assert kw["absorption_mask"].shape[1:] == (64, 4096)
-  check_bit_exact(kw, "systolic_lean")
+  check_bit_exact(kw)
 
 
 # ---- reduced precision at pjz's default geometry ------------------------------------------------------
