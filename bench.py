@@ -54,6 +54,8 @@ def parse():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  ap.add_argument("--no-reduced", action="store_true",
+                  help="skip the reduced-precision sub-record")
   ap.add_argument("--no-decomp", action="store_true",
                   help="skip the domain-decomposed (cfg5 metalens, y-slabs) record")
   ap.add_argument("--decomp-tt", type=int, default=2000)
@@ -480,6 +482,37 @@ def main():
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(res.nbytes)}
     assert np.isfinite(res).all()
 
+  # ---- reduced precision (pjz's default mode): same workload with fp16 storage, and pjz's own
+  # default height (128 - sum(pml_widths) = 96 z-cells, /root/reference/src/pjz/_field.py:52-58)
+  reduced = None
+  if not args.reduced and not args.no_reduced and args.workload == "bend" and world == 1:
+    reduced = []
+    for label, zz in (("cfg2 grid with fp16 storage (256x256x128)", 128),
+                      ("pjz default height, fp16 storage (256x256x96)", 96)):
+      from pjz_b200 import _field as glue
+      from pjz_b200 import workloads as W
+      eps, ports, params, omega = W.bend(total=(256, 256, zz), reduced=True)
+      if args.tt:
+        params = params._replace(tt=args.tt)
+      axis, pos, _ = ports[0]
+      kw, _, _ = glue.engine_inputs(eps, W.gaussian_port_source(eps, axis, pos), omega, pos, params)
+      kw = {k: (v.cuda() if hasattr(v, "cuda") else v) for k, v in kw.items()}
+      rinfo = fdtdz_jax.plan_info(**kw)
+      fdtdz_jax.fdtdz(**kw)
+      torch.cuda.synchronize()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(2):
+        r = fdtdz_jax.fdtdz(**kw)
+      b.record()
+      torch.cuda.synchronize()
+      rcells = 256 * 256 * zz
+      rv = rcells * params.tt * 2 / (a.elapsed_time(b) / 1e3) / 1e9
+      assert bool(torch.isfinite(r).all())
+      reduced.append({"value": rv, "unit": UNIT, "frac": rv * BYTES_PER_CELL[True] / measured_peak()[0],
+                      "bytes_per_cell_update": BYTES_PER_CELL[True],
+                      "config": {"workload": label, "fdtd_steps": params.tt, "plan": rinfo}})
+
   # ---- the sharded-domain record (all ranks take part) ----------------------------------------------
   decomp = None
   if not args.no_decomp:
@@ -510,8 +543,9 @@ def main():
     launches = (3 + 2 * tt) * args.steps
   per_launch_updates = cells * (tt if info["kernel"].startswith("systolic") else 0.5)
   # ncu DRAM bytes are only quoted for the kernel and configuration they were captured on
+  traffic = (traffic or {}).get("fp16" if args.reduced else "fp32")
   have_traffic = (traffic is not None and traffic.get("plan_kernel") == info["kernel"] and
-                  args.workload == "bend" and not args.reduced)
+                  args.workload == "bend")
   roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
               "frac": achieved / peak,
               "traffic": traffic["dram_bytes_per_cell_update"] * per_launch_updates
@@ -519,7 +553,15 @@ def main():
               "traffic_source": traffic["from"] if have_traffic else None,
               "kernel": dominant, "peak_source": peak_src,
               "algorithmic_bytes_per_launch": bpc * per_launch_updates,
-              "bytes_per_cell_update": bpc}
+              "bytes_per_cell_update": bpc,
+              # `frac` is a fraction of the SINGLE-PASS bound (60 / 30 algorithmic bytes per
+              # cell-update); the kernel is temporally blocked through L2, so its real HBM load is
+              # dram_frac = ncu DRAM bytes per cell-update x measured rate / peak -- HBM is not what
+              # limits it (issue latency is: issue_active_pct)
+              "dram_frac": traffic["dram_bytes_per_cell_update"] * per_gpu / peak
+              if have_traffic else None,
+              "l2_throughput_pct_ncu": traffic["l2_throughput_pct"] if have_traffic else None,
+              "issue_active_pct_ncu": traffic["issue_active_pct"] if have_traffic else None}
 
   cpu = None
   if world == 1 and not args.no_cpu:
@@ -538,7 +580,7 @@ def main():
                          "inputs larger than L2, no flush needed")),
                  "plan": info},
       "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-      "clocks": clocks, "decomp": decomp,
+      "clocks": clocks, "reduced_precision": reduced, "decomp": decomp,
   }
   print(json.dumps(line))
   if world > 1:

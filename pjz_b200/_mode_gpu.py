@@ -58,20 +58,31 @@ def _power_iteration(eps, omega, x, n):
   return w - 2.0 * rho - 0.1 * w.abs()
 
 
+_HOST_EIG = False     # set when this torch build has no batched CUDA geev (see _ritz)
+
+
 def _ritz(q, aq):
   """Rayleigh-Ritz on the block ``q`` (ww, N, p) with ``aq = op(q)``.  The waveguide operator is
-  not symmetric (the permittivity enters on one side only), so the small projected matrices go
-  through a general eigen-solver on the host (p <= ~16); eigenvalues are real for lossless
-  media.  Returns Ritz values (descending), unit-norm Ritz vectors and op(Ritz vectors)."""
-  t = torch.matmul(q.transpose(1, 2), aq).double().cpu().numpy()
-  thetas, ss = [], []
-  for tw in t:
-    lam, vec = np.linalg.eig(tw)
-    order = np.argsort(-lam.real)
-    thetas.append(lam.real[order])
-    ss.append(vec.real[:, order])
-  theta = torch.from_numpy(np.stack(thetas)).to(q.device, q.dtype)
-  s = torch.from_numpy(np.stack(ss)).to(q.device, q.dtype)
+  not symmetric (the permittivity enters on one side only), so the small projected matrices
+  (p <= ~16) go through a general eigen-solver: ``torch.linalg.eig`` batched over the frequencies
+  ON THE DEVICE (as the reference keeps its Rayleigh quotients inside ``lax.while_loop``,
+  /root/reference/src/pjz/_mode.py:129-138) -- nothing is copied to the host.  Eigenvalues are real
+  for lossless media.  Returns Ritz values (descending), unit-norm Ritz vectors, op(Ritz vectors)."""
+  global _HOST_EIG
+  t = torch.matmul(q.transpose(1, 2), aq).double()
+  lam = vec = None
+  if not _HOST_EIG:
+    try:
+      lam, vec = torch.linalg.eig(t)
+    except RuntimeError:                                   # no device geev in this build
+      _HOST_EIG = True
+  if lam is None:
+    lam, vec = torch.linalg.eig(t.cpu())
+    lam, vec = lam.to(q.device), vec.to(q.device)
+  lam_r, vec_r = lam.real, vec.real
+  order = torch.argsort(lam_r, dim=1, descending=True)
+  theta = torch.gather(lam_r, 1, order).to(q.dtype)
+  s = torch.gather(vec_r, 2, order[:, None, :].expand_as(vec_r)).to(q.dtype)
   x, ax = torch.matmul(q, s), torch.matmul(aq, s)
   nrm = torch.linalg.norm(x, dim=1, keepdim=True)
   return theta, x / nrm, ax / nrm

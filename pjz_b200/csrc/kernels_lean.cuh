@@ -47,6 +47,7 @@ constexpr int kLeanMaxWarps = 8;       // compute warps per CTA (+1 service warp
 constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
 constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
 constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
+constexpr int kSlabChunk = 4;          // y-slab sessions: planes between two pushes of an edge counter
 
 struct LeanCtl {
   unsigned avail;      // min over the three predecessor counters (raw, cumulative)
@@ -158,7 +159,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     const size_t pf_off = (size_t)ylo * g.Zp;
     unsigned pf_done = 0;
     const unsigned sweep_iters = (unsigned)X + 1u;
-    unsigned published = 0;
+    unsigned published = 0, pushed = 0;
     while (true) {
       const unsigned ex = ld_vol_s(&ctl.exited);
       unsigned dn = lane < NWt ? ld_vol_s(&ctl.wdone[lane]) : 0xffffffffu;
@@ -168,8 +169,18 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         if (lane == 0) {
           st_release_u32(my_prog, dn);
           if constexpr (SLAB) {
-            if (edge_lo) st_release_sys_u32(push_lo, dn);
-            if (edge_hi) st_release_sys_u32(push_hi, dn);
+            // The neighbour GPU sees this counter in steps of kSlabChunk planes (and at the end of
+            // every sweep): a system-scope release waits for the peer stores to be acknowledged
+            // across NVLink and would otherwise stall this warp's polling once per plane.  A
+            // consumer that sees the counter up to kSlabChunk - 1 planes late only trails further
+            // behind; no cycle of waits can close as long as max_lead >= kSlabChunk + 2
+            // (lean_configure enforces it).
+            if ((edge_lo || edge_hi) &&
+                (dn - pushed >= (unsigned)kSlabChunk || dn % (unsigned)X == 0u || ex == (unsigned)NW)) {
+              if (edge_lo) st_release_sys_u32(push_lo, dn);
+              if (edge_hi) st_release_sys_u32(push_hi, dn);
+              pushed = dn;
+            }
           }
         }
         published = dn;
@@ -177,7 +188,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         break;
       }
       unsigned v = 0xffffffffu;
-      if (lane < 5) v = SLAB ? ld_relaxed_sys_u32(watch) : ld_relaxed_gpu_u32(watch);
+      if (SLAB && ((lane == 0 && t == 0) || (lane == 2 && t == NT - 1)))
+        v = ld_relaxed_sys_u32(watch);               // a mirror slot: written by the neighbour GPU
+      else if (lane < 5) v = ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
                      v4 = __shfl_sync(0xffffffffu, v, 4);
@@ -673,9 +686,11 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         }
         // every store of sweep indices <= i has been issued by this warp
         __syncwarp();
+        // (slab edges: the peer stores above are ordered before the mirror counter by the service
+        // warp's st.release.sys; a system-scope fence here, in every warp and plane of an edge tile,
+        // took a 4096 x 512 x 128 slab from 69 to 31 Gcell/s)
         if (lane == 0) {
-          if (SLAB && (edge_lo || edge_hi)) __threadfence_system();   // peer stores before the counter
-          else __threadfence_block();
+          __threadfence_block();
           st_vol_s(&ctl.wdone[w], base_mine + (unsigned)i);
         }
       } else if (w > 0 && lane == 0) {
@@ -739,7 +754,11 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   cfg->threads = 32 * (lean_warps(widest) + 1);
   cfg->smem_bytes = (int)lean_smem_bytes(g, widest);
   cfg->max_lead = 10;
-  cfg->pf_ahead = 6;
+  // L2 prefetch by the service warp: OFF.  Measured on cfg2 (round 2, bench.py, 20 000 steps):
+  // 103.4 Gcell/s with 6 planes of cp.async.bulk.prefetch.L2 ahead of the ring, 102.3 with 12,
+  // 119.5 with none -- the ring's own copies run a plane (2.7 us) ahead, which already covers
+  // the HBM latency, and the prefetches compete with them for L2 bandwidth and power.
+  cfg->pf_ahead = 0;
   cfg->svc_sleep_ns = 200;
   cfg->spin_ns_max = 160;
   cfg->discard = 1;

@@ -428,6 +428,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
       const float4* const pc = hcur + C::HRows * LPC + K * h * psi_row + (has_psi ? slot : 0);
       const float4* const tail = hcur + C::HRows * LPC + 4 * CW * psi_row;
       float ex[K][VW], ey[K][VW], ez[K][VW], hx[K][VW], hy[K][VW], hz[K][VW], psx[K][VW], psy[K][VW];
+      float4 phx[K], phy[K], phz[K];               // the new H in storage format (boundary slot, stores)
       {
         float exn[VW], ezn[VW], ah[VW], bh[VW], ikh[VW];
 #pragma unroll
@@ -464,8 +465,12 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
             const float ex_yp = (k + 1 < K) ? ex[(k + 1) % K][v] : exn[v];
             h_cell(ex[k][v], ey[k][v], ez[k][v], exz, eyz, ez_yp, ex_yp, eyx[v], ezx[v], ah[v], bh[v],
                    ikh[v], dt, psx[k][v], psy[k][v], hx[k][v], hy[k][v], hz[k][v]);
-            hx[k][v] = round_store<T>(hx[k][v]); hy[k][v] = round_store<T>(hy[k][v]);
-            hz[k][v] = round_store<T>(hz[k][v]);
+          }
+          // round to the storage type by packing (one F2FP per pair of halves) and keep the packed
+          // vectors for the boundary slot and the stores; the E half-step uses the rounded values
+          phx[k] = pack(hx[k], T()); phy[k] = pack(hy[k], T()); phz[k] = pack(hz[k], T());
+          if constexpr (sizeof(T) == 2) {
+            unpack(phx[k], hx[k], T()); unpack(phy[k], hy[k], T()); unpack(phz[k], hz[k], T());
           }
         }
       }
@@ -481,8 +486,8 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
           if constexpr (STATS) st_rc += clock64() - c0;
           if (!ok) break;
         }
-        xs[0] = pack(hz[K - 1], T());
-        xs[LPC] = pack(hx[K - 1], T());
+        xs[0] = phz[K - 1];
+        xs[LPC] = phx[K - 1];
         __syncwarp();
         if (lane == 0) st_vol_s(&ctl.hcnt[w], kk + 1u);
       }
@@ -554,8 +559,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
               add_source<VW>(g, p.src, w0, w1, P, yk[k], q, ex[k], ey[k], ez[k]);
             }
             const unsigned o = vP + tv[k];
-            __stcg(wHx + o, pack(hx[k], T())); __stcg(wHy + o, pack(hy[k], T()));
-            __stcg(wHz + o, pack(hz[k], T()));
+            __stcg(wHx + o, phx[k]); __stcg(wHy + o, phy[k]); __stcg(wHz + o, phz[k]);
             __stcg(wEx + o, pack(ex[k], T())); __stcg(wEy + o, pack(ey[k], T()));
             __stcg(wEz + o, pack(ez[k], T()));
             if (has_psi) {
@@ -640,7 +644,7 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   cfg->threads = 32 * (nw + 1);
   cfg->smem_bytes = (int)(warp_bytes * nw);
   cfg->max_lead = 10;
-  cfg->pf_ahead = 6;
+  cfg->pf_ahead = 0;                             // see lean_configure: 126.2 vs 122.2 Gcell/s (fp16 cfg2)
   cfg->svc_sleep_ns = 200;
   cfg->spin_ns_max = 160;
   // L2 discard of consumed lines: off by default here.  With these short columns (and half the

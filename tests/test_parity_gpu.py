@@ -345,6 +345,56 @@ def test_xla_custom_call_entry_and_internal_workspace():
   np.testing.assert_array_equal(out2.cpu().numpy(), want)
 
 
+def test_xla_status_returning_custom_call_reports_failures(tmp_path):
+  """b200fdtd_xla_custom_call_status: the result is computed on success; a bad descriptor or a
+  scratch buffer smaller than this device's plan needs sets the XLA status (here a stand-in
+  `XlaCustomCallStatusSetFailure` loaded into the process, as jaxlib would provide it) instead of
+  returning garbage silently."""
+  import struct
+  import subprocess
+  stub_c = tmp_path / "xla_status_stub.c"
+  stub_c.write_text(
+      "#include <string.h>\n#include <stddef.h>\n"
+      "void XlaCustomCallStatusSetFailure(void* s, const char* m, size_t n) {\n"
+      "  if (n > 255) n = 255; memcpy(s, m, n); ((char*)s)[n] = 0; }\n")
+  stub_so = tmp_path / "libxla_status_stub.so"
+  subprocess.check_call(["/usr/bin/gcc", "-shared", "-fPIC", str(stub_c), "-o", str(stub_so)])
+  ctypes.CDLL(str(stub_so), mode=ctypes.RTLD_GLOBAL)
+  kw = random_problem(domain=(16, 12, 16), tt=10, seed=3, output_steps=(4, 10, 3))
+  want = run_gpu(kw)
+  d = fdtdz_jax.make_desc(**kw)
+  L = fdtdz_jax.lib()
+  L.b200fdtd_workspace_bytes.restype = ctypes.c_size_t
+  need = L.b200fdtd_workspace_bytes(ctypes.byref(d))
+  ins = [torch.from_numpy(np.ascontiguousarray(kw[k], np.float32)).cuda() for k in (
+      "epsilon", "source_field", "source_waveform", "absorption_mask", "pml_kappa", "pml_sigma",
+      "pml_alpha")]
+  out = torch.zeros(want.shape, device="cuda")
+  ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+  bufs = (ctypes.c_void_p * 9)(*([t.data_ptr() for t in ins] + [out.data_ptr(), ws.data_ptr()]))
+  fn = L.b200fdtd_xla_custom_call_status
+  fn.restype = None
+  fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+  desc_bytes = ctypes.string_at(ctypes.byref(d), ctypes.sizeof(d))
+  status = ctypes.create_string_buffer(256)
+  opaque = desc_bytes + struct.pack("<Q", need)
+  fn(None, bufs, opaque, len(opaque), status)
+  torch.cuda.synchronize()
+  assert status.value == b""
+  np.testing.assert_array_equal(out.cpu().numpy(), want)
+  # scratch declared at trace time is smaller than this device's plan needs
+  out.zero_()
+  opaque = desc_bytes + struct.pack("<Q", need // 2)
+  fn(None, bufs, opaque, len(opaque), status)
+  torch.cuda.synchronize()
+  assert b"scratch declared at trace time" in status.value
+  assert not out.any()
+  # malformed opaque
+  status = ctypes.create_string_buffer(256)
+  fn(None, bufs, desc_bytes[:-4], len(desc_bytes) - 4, status)
+  assert b"opaque must be a b200fdtd_desc" in status.value
+
+
 def test_two_streams_are_independent():
   kw1 = random_problem(domain=(24, 20, 16), tt=20, seed=41)
   kw2 = random_problem(domain=(24, 20, 16), tt=20, seed=42)
