@@ -47,7 +47,7 @@ constexpr int kLeanMaxWarps = 8;       // compute warps per CTA (+1 service warp
 constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
 constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
 constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
-constexpr int kSlabChunk = 4;          // y-slab sessions: planes between two pushes of an edge counter
+constexpr int kSlabChunk = 1;          // y-slab sessions: planes between two pushes of an edge counter
 
 struct LeanCtl {
   unsigned avail;      // min over the three predecessor counters (raw, cumulative)
@@ -81,6 +81,8 @@ __device__ __forceinline__ void discard_l2_line(const void* p) {
 struct SlabPeers {
   long long delta_lo, delta_hi;    // neighbour's workspace base minus mine (bytes); 0 = myself
   int enabled;
+  int chunk;                       // planes between two pushes of an edge counter (B200FDTD_SLAB_CHUNK)
+  int diag;                        // B200FDTD_SLAB_DIAG = 4: print the courier's push latencies
 };
 
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -139,6 +141,50 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   if (tid == 0) ctl.ok = 1u;
   __syncthreads();
 
+  // ==================================== courier CTA ===============================================
+  // Slab sessions: one extra CTA (block index S*NT, on an SM no tile uses) forwards the progress
+  // counters of the slab's edge tiles to the neighbour GPUs' mirror slots.  A system-scope release
+  // costs ~3 us from inside a tile's CTA (measured: 5 700 cycles per st.release.sys, against a plane
+  // time of 2.4 us; with the pushes in the service warp or in a tenth warp of the edge tiles a
+  // 1024 x 512 x 128 slab ran at 67-79 Gcell/s instead of 106), so no warp of a tile ever executes
+  // one.  Ordering of the peer DATA stores before the forwarded counter is by causality: the warps'
+  // peer stores -> fence.cta -> wdone -> the tile's service warp reads, st.release.gpu(counter) ->
+  // courier ld.acquire.gpu(counter) -> st.release.sys(mirror slot).
+  if (SLAB && blockIdx.x == (unsigned)(S * NT)) {
+    // counter c = side * S + stage (side 0: tile 0 -> low neighbour; 1: tile NT-1 -> high
+    // neighbour), one per THREAD, dealt across the warps first: every warp polls its lanes'
+    // counters together and pays one system-scope fence per round, however many of them moved
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int c = lane * nwarps + (tid >> 5);
+    const bool mine = c < 2 * S;
+    const int side = mine ? c / S : 0, jj = mine ? c % S : 0;
+    const unsigned* const src = sync + ((size_t)jj * NT + (side == 0 ? 0 : NT - 1)) * kSysFlagStride;
+    unsigned* const dst = side == 0 ? peer_ptr(mirror_hi + (size_t)jj * kSysFlagStride, peers.delta_lo)
+                                    : peer_ptr(mirror_lo + (size_t)jj * kSysFlagStride, peers.delta_hi);
+    const int left = g.tt - g.n0 - jj;                       // steps n0+jj, n0+jj+S, ... < tt
+    const unsigned final_count = (mine && left > 0) ? (unsigned)((left + S - 1) / S) * (unsigned)X : 0u;
+    unsigned last = 0, spins = 0;
+    long long t_st = 0;
+    unsigned n_st = 0;
+    while (__any_sync(0xffffffffu, last < final_count)) {
+      const unsigned v = last < final_count ? ld_acquire_u32(src) : last;
+      if (__any_sync(0xffffffffu, v != last)) {
+        const long long c0 = clock64();
+        if (v != last) st_release_sys_u32(dst, v);
+        __syncwarp();
+        t_st += clock64() - c0; ++n_st;
+        last = v;
+      } else {
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0 && ld_relaxed_gpu_u32(status) != 0) break;     // somebody gave up
+      }
+    }
+    if ((peers.diag & 4) && lane == 0 && (tid >> 5) < 2)
+      printf("courier warp %d: %u push rounds, %.0f cycles each\n", tid >> 5, n_st,
+             (double)t_st / (n_st ? n_st : 1));
+    return;
+  }
+
   // =================================== service warp ==============================================
   if (w == NW) {
     const int jp = (j + S - 1) % S, jn = (j + 1) % S;
@@ -150,16 +196,13 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     }
     if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
     if (lane == 4) watch = status;
-    // my counter as the neighbours see it: their mirror slots (same layout, their workspace)
-    unsigned* const push_lo = peer_ptr(mirror_hi + (size_t)j * kSysFlagStride, peers.delta_lo);
-    unsigned* const push_hi = peer_ptr(mirror_lo + (size_t)j * kSysFlagStride, peers.delta_hi);
     // L2 prefetch duty: lanes 8..16 own one array each (E0..2, H0..2 of the read set, B0..2).
     const int ylo = max(y0 - 1, 0), yhi = min(y0 + Yt, Y - 1);
     const unsigned pf_bytes = (unsigned)((yhi - ylo + 1) * g.Zp * (int)sizeof(float));
     const size_t pf_off = (size_t)ylo * g.Zp;
     unsigned pf_done = 0;
     const unsigned sweep_iters = (unsigned)X + 1u;
-    unsigned published = 0, pushed = 0;
+    unsigned published = 0;
     while (true) {
       const unsigned ex = ld_vol_s(&ctl.exited);
       unsigned dn = lane < NWt ? ld_vol_s(&ctl.wdone[lane]) : 0xffffffffu;
@@ -168,20 +211,6 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       if (dn != published) {
         if (lane == 0) {
           st_release_u32(my_prog, dn);
-          if constexpr (SLAB) {
-            // The neighbour GPU sees this counter in steps of kSlabChunk planes (and at the end of
-            // every sweep): a system-scope release waits for the peer stores to be acknowledged
-            // across NVLink and would otherwise stall this warp's polling once per plane.  A
-            // consumer that sees the counter up to kSlabChunk - 1 planes late only trails further
-            // behind; no cycle of waits can close as long as max_lead >= kSlabChunk + 2
-            // (lean_configure enforces it).
-            if ((edge_lo || edge_hi) &&
-                (dn - pushed >= (unsigned)kSlabChunk || dn % (unsigned)X == 0u || ex == (unsigned)NW)) {
-              if (edge_lo) st_release_sys_u32(push_lo, dn);
-              if (edge_hi) st_release_sys_u32(push_hi, dn);
-              pushed = dn;
-            }
-          }
         }
         published = dn;
       } else if (ex == (unsigned)NW) {
@@ -189,7 +218,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       }
       unsigned v = 0xffffffffu;
       if (SLAB && ((lane == 0 && t == 0) || (lane == 2 && t == NT - 1)))
-        v = ld_relaxed_sys_u32(watch);               // a mirror slot: written by the neighbour GPU
+        v = ld_relaxed_sys_u32(watch);               // a mirror slot: written by the neighbour GPU's courier
       else if (lane < 5) v = ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
@@ -783,7 +812,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
     *why = "kernel does not fit on an SM";
     return false;
   }
-  const long long capacity = (long long)occ * sms;
+  const long long capacity = (long long)occ * sms - (slab ? 1 : 0);   // (a slab's courier CTA)
   if (ntiles > capacity) { *why = "more y-tiles than co-resident CTAs"; return false; }
   int stages = (int)(capacity / ntiles);
   const long long plane_bytes = g.P * 4ll * 15;
@@ -810,11 +839,19 @@ inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& c
   Ptrs<float> pp = p;
   SystolicCfg cc = cfg;
   SlabPeers sp;
-  sp.delta_lo = 0; sp.delta_hi = 0; sp.enabled = 0;
-  if (slab) sp = *peers;
-  void* args[] = {&gg, &pp, &cc, &sync, &sp};
-  e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles), dim3(cfg.threads), args,
-                                  cfg.smem_bytes, st);
+  sp.delta_lo = 0; sp.delta_hi = 0; sp.enabled = 0; sp.chunk = kSlabChunk; sp.diag = 0;
+  if (slab) {
+    sp = *peers;
+    sp.chunk = kSlabChunk;
+    if (const char* e = getenv("B200FDTD_SLAB_CHUNK")) sp.chunk = atoi(e) < 1 ? 1 : atoi(e);
+    // a consumer may see an edge counter up to chunk - 1 planes late: keep the throttle wider
+    if (sp.chunk + 6 > cc.max_lead) cc.max_lead = sp.chunk + 6;
+    sp.diag = 0;
+    if (const char* e = getenv("B200FDTD_SLAB_DIAG")) sp.diag = atoi(e) & 4;
+  }
+  void* args[] = {&gg, &pp, &cc, &sync, &sp};   // (cc, sp finalised above)
+  e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles + (slab ? 1 : 0)), dim3(cfg.threads),
+                                  args, cfg.smem_bytes, st);
   if (e != cudaSuccess) return (int)e;
   systolic_check_kernel<<<1, 1, 0, st>>>(sync + (size_t)cfg.stages * cfg.ntiles * kSysFlagStride);
   return (int)cudaGetLastError();
