@@ -47,7 +47,7 @@ constexpr int kLeanMaxWarps = 8;       // compute warps per CTA (+1 service warp
 constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
 constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
 constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
-constexpr int kSlabChunk = 1;          // y-slab sessions: planes between two pushes of an edge counter
+constexpr int kSlabMaxStages = 36;     // y-slab sessions: most pipeline stages (courier counter table)
 
 struct LeanCtl {
   unsigned avail;      // min over the three predecessor counters (raw, cumulative)
@@ -55,6 +55,7 @@ struct LeanCtl {
   unsigned ok;         // 0 once any CTA gave up
   unsigned front;      // cumulative iteration index warp 0 has reached (L2 prefetch cursor)
   unsigned exited;     // compute warps that have left the time loop
+  unsigned cour;       // slab edge tiles: planes of the step two back that the courier has carried off
   unsigned wdone[kLeanMaxWarps + 1];   // per warp: cumulative finished sweep indices
   unsigned hcnt[kLeanMaxWarps + 1];    // per warp: iterations whose boundary H is in the slot
   unsigned rcnt[kLeanMaxWarps + 1];    // per warp: iterations the next warp has consumed
@@ -72,16 +73,16 @@ __device__ __forceinline__ void discard_l2_line(const void* p) {
 // The neighbouring GPUs run the same kernel on the same local geometry and behave exactly like
 // the tiles t-1 / t+1 of the periodic single-GPU run: the warp that owns the slab's last column
 // stores its new (E, H, psiH) also into the HIGH neighbour's low ghost column, the warp that owns
-// the first column stores (Ex, Ez) into the LOW neighbour's high ghost column, and the service
-// warp of an edge tile publishes its progress counter also into the neighbour's mirror slot
-// (st.release.sys behind the warps' system-scope fences).  Consumers read ghost data and mirror
+// the first column stores (Ex, Ez) into the LOW neighbour's high ghost column, and a COURIER CTA
+// forwards the edge tiles' progress counters into the neighbours' mirror slots with
+// st.release.sys (see the courier block in the kernel).  Consumers read ghost data and mirror
 // counters from their OWN memory, so the k+3 rule and the WAR argument of DESIGN.md 4.5 carry over
 // with "tile t-1 / t+1" = the neighbour's edge tile.  All workspaces have the same layout, so a
 // peer address is the local address plus one byte offset per side.
 struct SlabPeers {
   long long delta_lo, delta_hi;    // neighbour's workspace base minus mine (bytes); 0 = myself
   int enabled;
-  int chunk;                       // planes between two pushes of an edge counter (B200FDTD_SLAB_CHUNK)
+  int edge_lead;                   // extra planes of max_lead for the tiles next to a slab edge
   int diag;                        // B200FDTD_SLAB_DIAG = 4: print the courier's push latencies
 };
 
@@ -134,7 +135,13 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   unsigned* const my_prog = sync + ((size_t)j * NT + t) * kSysFlagStride;
   unsigned* const mirror_lo = status + kSysFlagStride;            // [S]: low neighbour's last tile
   unsigned* const mirror_hi = mirror_lo + (size_t)S * kSysFlagStride;   // high neighbour's first tile
+  unsigned* const cour_lo = mirror_hi + (size_t)S * kSysFlagStride;     // [S]: courier progress, low side
+  unsigned* const cour_hi = cour_lo + (size_t)S * kSysFlagStride;       // ... high side
   const bool edge_lo = SLAB && t == 0, edge_hi = SLAB && t == NT - 1;
+  // A neighbour GPU's counter arrives ~6 us (two planes) later than a local tile's, so the tiles
+  // an edge's delay reaches within one round (one tile further per stage) may run further ahead of
+  // their successor stage before they are throttled; the L2 window grows for those tiles only.
+  const int max_lead = cfg.max_lead + ((SLAB && (t < S || t >= NT - S)) ? peers.edge_lead : 0);
 
   if (tid < (int)(sizeof(LeanCtl) / sizeof(unsigned))) reinterpret_cast<unsigned*>(&ctl)[tid] = 0u;
   __syncthreads();
@@ -142,46 +149,96 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   __syncthreads();
 
   // ==================================== courier CTA ===============================================
-  // Slab sessions: one extra CTA (block index S*NT, on an SM no tile uses) forwards the progress
-  // counters of the slab's edge tiles to the neighbour GPUs' mirror slots.  A system-scope release
-  // costs ~3 us from inside a tile's CTA (measured: 5 700 cycles per st.release.sys, against a plane
-  // time of 2.4 us; with the pushes in the service warp or in a tenth warp of the edge tiles a
-  // 1024 x 512 x 128 slab ran at 67-79 Gcell/s instead of 106), so no warp of a tile ever executes
-  // one.  Ordering of the peer DATA stores before the forwarded counter is by causality: the warps'
-  // peer stores -> fence.cta -> wdone -> the tile's service warp reads, st.release.gpu(counter) ->
-  // courier ld.acquire.gpu(counter) -> st.release.sys(mirror slot).
+  // Slab sessions: one extra CTA (block index S*NT, on an SM no tile uses) carries the halo to the
+  // neighbour GPUs.  One warp per edge counter (side x stage): it watches the counter the edge
+  // tile publishes (ld.acquire.gpu), copies the planes that counter newly covers -- the slab's
+  // last owned column (E, H, psiH) into the HIGH neighbour's low ghost column, the first owned
+  // column (Ex, Ez) into the LOW neighbour's high ghost column, read from the local L2, stored
+  // through the peer mapping -- and then forwards the counter into the neighbour's mirror slot
+  // with st.release.sys, which orders the warp's own peer stores before it.
+  // Why not from the tiles themselves: a system-scope release costs ~3 us (5 400-6 000 cycles
+  // measured against a plane time of 2.4 us) and stalls the memory pipeline of the SM that issues it
+  // (1024 x 512 x 128 slab, one GPU wrapped onto itself: 31 Gcell/s with a system fence in the storing
+  // warps, 79 with the pushes in the edge tiles' service warp, 67-72 with a tenth warp, 106 with
+  // counters forwarded from here), and peer stores issued by a compute warp throttle that warp
+  // across NVLink (two GPUs: 80 Gcell/s per GPU against 106 wrapped).  Here both sit on an idle SM
+  // and only add latency, which the pipeline's slack (max_lead) absorbs.
   if (SLAB && blockIdx.x == (unsigned)(S * NT)) {
-    // counter c = side * S + stage (side 0: tile 0 -> low neighbour; 1: tile NT-1 -> high
-    // neighbour), one per THREAD, dealt across the warps first: every warp polls its lanes'
-    // counters together and pays one system-scope fence per round, however many of them moved
-    const int nwarps = (int)(blockDim.x >> 5);
-    const int c = lane * nwarps + (tid >> 5);
-    const bool mine = c < 2 * S;
-    const int side = mine ? c / S : 0, jj = mine ? c % S : 0;
-    const unsigned* const src = sync + ((size_t)jj * NT + (side == 0 ? 0 : NT - 1)) * kSysFlagStride;
-    unsigned* const dst = side == 0 ? peer_ptr(mirror_hi + (size_t)jj * kSysFlagStride, peers.delta_lo)
-                                    : peer_ptr(mirror_lo + (size_t)jj * kSysFlagStride, peers.delta_hi);
-    const int left = g.tt - g.n0 - jj;                       // steps n0+jj, n0+jj+S, ... < tt
-    const unsigned final_count = (mine && left > 0) ? (unsigned)((left + S - 1) / S) * (unsigned)X : 0u;
-    unsigned last = 0, spins = 0;
-    long long t_st = 0;
-    unsigned n_st = 0;
-    while (__any_sync(0xffffffffu, last < final_count)) {
-      const unsigned v = last < final_count ? ld_acquire_u32(src) : last;
-      if (__any_sync(0xffffffffu, v != last)) {
+    __shared__ unsigned cour_last[2 * kSlabMaxStages];       // count already carried, per counter
+    const int nwarps = (int)(blockDim.x >> 5), wid = tid >> 5;
+    for (int c = tid; c < 2 * S; c += (int)blockDim.x) cour_last[c] = 0u;
+    __syncthreads();
+    const unsigned PVn = (unsigned)Y * ZQ, PPn = (unsigned)Y * g.npg;
+    unsigned spins = 0, n_push = 0;
+    long long t_push = 0;
+    bool busy = true, give_up = false;
+    while (busy && !give_up) {
+      busy = false;
+      for (int c = wid; c < 2 * S; c += nwarps) {            // counter c = side * S + stage
+        const unsigned last_c = cour_last[c];
+        const int side = c / S, jj = c % S;
+        const int left = g.tt - g.n0 - jj;                   // steps n0+jj, n0+jj+S, ... < tt
+        const unsigned final_count = left > 0 ? (unsigned)((left + S - 1) / S) * (unsigned)X : 0u;
+        if (last_c >= final_count) continue;
+        busy = true;
+        const unsigned v = ld_acquire_u32(sync + ((size_t)jj * NT + (side == 0 ? 0 : NT - 1)) * kSysFlagStride);
+        if (v == last_c) continue;
         const long long c0 = clock64();
-        if (v != last) st_release_sys_u32(dst, v);
+        const long long delta = side == 0 ? peers.delta_lo : peers.delta_hi;
+        const unsigned ysrc = (unsigned)(side == 0 ? g.ylo : g.yhi - 1);       // my edge column
+        const unsigned ydst = (unsigned)(side == 0 ? g.yhi : g.ylo - 1);       // the neighbour's ghost
+        for (unsigned cnt = last_c + 1u; cnt <= v; ++cnt) {
+          const unsigned m = (cnt - 1u) / (unsigned)X, i = (cnt - 1u) % (unsigned)X + 1u;
+          const int n = g.n0 + jj + (int)m * S;
+          const unsigned P = (unsigned)wrapi(wrapi(n % X - 1, X) + (int)i, X);   // plane of sweep index i
+          const int wb = (n & 1) ^ 1;
+          const unsigned so = P * PVn + ysrc * ZQ + lane, dof = P * PVn + ydst * ZQ + lane;
+          if (side == 0) {                                   // first owned column -> (Ex, Ez)
+            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p.Es[wb][0]) + so);
+            const float4 a2 = __ldcg(reinterpret_cast<const float4*>(p.Es[wb][2]) + so);
+            __stcg(peer_ptr(reinterpret_cast<float4*>(p.Es[wb][0]) + dof, delta), a0);
+            __stcg(peer_ptr(reinterpret_cast<float4*>(p.Es[wb][2]) + dof, delta), a2);
+          } else {                                           // last owned column -> E, H, psiH
+            float4 r[6];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              r[cc] = __ldcg(reinterpret_cast<const float4*>(p.Es[wb][cc]) + so);
+              r[3 + cc] = __ldcg(reinterpret_cast<const float4*>(p.Hs[wb][cc]) + so);
+            }
+            float4 ps[2];
+            const bool pl = lane < g.npg;
+            const unsigned pso = P * PPn + ysrc * g.npg + lane, pdo = P * PPn + ydst * g.npg + lane;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+              if (pl) ps[cc] = __ldcg(reinterpret_cast<const float4*>(p.psiHs[wb][cc]) + pso);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              __stcg(peer_ptr(reinterpret_cast<float4*>(p.Es[wb][cc]) + dof, delta), r[cc]);
+              __stcg(peer_ptr(reinterpret_cast<float4*>(p.Hs[wb][cc]) + dof, delta), r[3 + cc]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+              if (pl) __stcg(peer_ptr(reinterpret_cast<float4*>(p.psiHs[wb][cc]) + pdo, delta), ps[cc]);
+          }
+        }
         __syncwarp();
-        t_st += clock64() - c0; ++n_st;
-        last = v;
-      } else {
-        __nanosleep(100);
-        if ((++spins & 1023u) == 0 && ld_relaxed_gpu_u32(status) != 0) break;     // somebody gave up
+        if (lane == 0) {
+          // the edge column's planes up to v have been read: the step after next may overwrite them
+          st_release_u32((side == 0 ? cour_lo : cour_hi) + (size_t)jj * kSysFlagStride, v);
+          unsigned* const mirror = side == 0 ? peer_ptr(mirror_hi + (size_t)jj * kSysFlagStride, peers.delta_lo)
+                                             : peer_ptr(mirror_lo + (size_t)jj * kSysFlagStride, peers.delta_hi);
+          st_release_sys_u32(mirror, v);
+        }
+        __syncwarp();
+        t_push += clock64() - c0; ++n_push;
+        if (lane == 0) cour_last[c] = v;
+        __syncwarp();
       }
+      if ((++spins & 4095u) == 0 && ld_relaxed_gpu_u32(status) != 0) give_up = true;   // somebody gave up
     }
-    if ((peers.diag & 4) && lane == 0 && (tid >> 5) < 2)
-      printf("courier warp %d: %u push rounds, %.0f cycles each\n", tid >> 5, n_st,
-             (double)t_st / (n_st ? n_st : 1));
+    if ((peers.diag & 4) && lane == 0 && wid < 2)
+      printf("courier warp %d: %u pushes, %.0f cycles each\n", wid, n_push,
+             (double)t_push / (n_push ? n_push : 1));
     return;
   }
 
@@ -196,6 +253,11 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     }
     if (lane == 3) watch = sync + ((size_t)jn * NT + t) * kSysFlagStride;
     if (lane == 4) watch = status;
+    // slab edge tiles: the courier's progress on the step two before this CTA's (always stage j - 2)
+    const int jq = (j + 2 * S - 2) % S;
+    if (lane == 5) watch = cour_lo + (size_t)jq * kSysFlagStride;
+    if (lane == 6) watch = cour_hi + (size_t)jq * kSysFlagStride;
+    const bool watch_cour = (lane == 5 && edge_lo) || (lane == 6 && edge_hi);
     // L2 prefetch duty: lanes 8..16 own one array each (E0..2, H0..2 of the read set, B0..2).
     const int ylo = max(y0 - 1, 0), yhi = min(y0 + Yt, Y - 1);
     const unsigned pf_bytes = (unsigned)((yhi - ylo + 1) * g.Zp * (int)sizeof(float));
@@ -219,7 +281,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
       unsigned v = 0xffffffffu;
       if (SLAB && ((lane == 0 && t == 0) || (lane == 2 && t == NT - 1)))
         v = ld_relaxed_sys_u32(watch);               // a mirror slot: written by the neighbour GPU's courier
-      else if (lane < 5) v = ld_relaxed_gpu_u32(watch);
+      else if (lane < 5 || watch_cour) v = ld_relaxed_gpu_u32(watch);
       const unsigned v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
                      v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3),
                      v4 = __shfl_sync(0xffffffffu, v, 4);
@@ -227,6 +289,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
         st_vol_s(&ctl.avail, min(v0, min(v1, v2)));
         st_vol_s(&ctl.next, v3);
         if (v4 != 0) st_vol_s(&ctl.ok, 0u);
+      }
+      if constexpr (SLAB) {
+        const unsigned v5 = __shfl_sync(0xffffffffu, v, 5), v6 = __shfl_sync(0xffffffffu, v, 6);
+        if (lane == 0) st_vol_s(&ctl.cour, min(v5, v6));
       }
       const unsigned front = ld_vol_s(&ctl.front);
       const unsigned want = front + 1u + (unsigned)cfg.pf_ahead;
@@ -281,13 +347,6 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const unsigned pvB = (unsigned)yB * g.npg + (has_psi ? slot : 0);
   const bool top = q + 1 == ZQ, bottom = q == 0;
   const bool discA = cA >= 2 && cA <= Yt - 1, discB = cB >= 2 && cB <= Yt - 1;
-  // slab edges: the first owned column is column B of warp 0 in tile 0; the last owned column is
-  // tile-local column Yt of the last tile
-  const bool push_lo_B = edge_lo && w == 0 && doHB;
-  const bool push_hi_A = edge_hi && cA == Yt && ownA, push_hi_B = edge_hi && cB == Yt;
-  const unsigned gv_lo = (unsigned)g.yhi * ZQ + q;               // neighbour's HIGH ghost column
-  const unsigned gv_hi = (unsigned)(SLAB ? g.ylo - 1 : 0) * ZQ + q;   // neighbour's LOW ghost column
-  const unsigned gp_hi = (unsigned)(SLAB ? g.ylo - 1 : 0) * g.npg + (has_psi ? slot : 0);
 
   float4* const wbase = smem + (size_t)w * warp_f4;
   float4* const hbase = wbase + 3 * eslot_f4;
@@ -395,8 +454,16 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     // run more than max_lead indices ahead of the next stage (keeps the window inside L2).
     auto wait_deps = [&](int it) -> bool {
       const unsigned need = has_prev ? base_prev + (unsigned)min(it + 2, X) : 0u;
-      const int lead = min(it, X) - 1 - cfg.max_lead;
+      const int lead = min(it, X) - 1 - max_lead;
       const unsigned need_next = (has_next && lead > 0) ? base_mine + (unsigned)lead : 0u;
+      if constexpr (SLAB) {
+        // An edge tile overwrites (iteration it - 1, same buffer set) the plane that the step two
+        // back wrote at its sweep index it + 1: the courier must have carried it off first.
+        if ((edge_lo || edge_hi) && n - 2 >= g.n0) {
+          const unsigned need_c = (unsigned)((n - 2 - g.n0) / S) * (unsigned)X + (unsigned)min(it + 1, X);
+          if (!spin([&]() { return ld_vol_s(&ctl.cour) >= need_c; })) return false;
+        }
+      }
       if constexpr (STATS) {
         const long long c0 = clock64();
         const bool r0 = spin([&]() { return ld_vol_s(&ctl.avail) >= need; });
@@ -651,20 +718,6 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvA), arr_to_f4(psxA)); __stcg(wPy + (pP + pvA), arr_to_f4(psyA));
             __stcg(ePx + (pP + pvA), arr_to_f4(qsx)); __stcg(ePy + (pP + pvA), arr_to_f4(qsy));
           }
-          if constexpr (SLAB) {
-            if (push_hi_A) {                         // -> the high neighbour's low ghost column
-              const unsigned og = vP + gv_hi;
-              const long long dl = peers.delta_hi;
-              __stcg(peer_ptr(wHx + og, dl), arr_to_f4(hxA)); __stcg(peer_ptr(wHy + og, dl), arr_to_f4(hyA));
-              __stcg(peer_ptr(wHz + og, dl), arr_to_f4(hzA));
-              __stcg(peer_ptr(wEx + og, dl), arr_to_f4(exA)); __stcg(peer_ptr(wEy + og, dl), arr_to_f4(eyA));
-              __stcg(peer_ptr(wEz + og, dl), arr_to_f4(ezA));
-              if (has_psi) {
-                __stcg(peer_ptr(wPx + (pP + gp_hi), dl), arr_to_f4(psxA));
-                __stcg(peer_ptr(wPy + (pP + gp_hi), dl), arr_to_f4(psyA));
-              }
-            }
-          }
           if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yA, q, exA, eyA, ezA, p.proj);
         }
         if (doHB) {
@@ -692,32 +745,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
             __stcg(wPx + (pP + pvB), arr_to_f4(psxB)); __stcg(wPy + (pP + pvB), arr_to_f4(psyB));
             __stcg(ePx + (pP + pvB), arr_to_f4(qsx)); __stcg(ePy + (pP + pvB), arr_to_f4(qsy));
           }
-          if constexpr (SLAB) {
-            if (push_hi_B) {                         // -> the high neighbour's low ghost column
-              const unsigned og = vP + gv_hi;
-              const long long dl = peers.delta_hi;
-              __stcg(peer_ptr(wHx + og, dl), arr_to_f4(hxB)); __stcg(peer_ptr(wHy + og, dl), arr_to_f4(hyB));
-              __stcg(peer_ptr(wHz + og, dl), arr_to_f4(hzB));
-              __stcg(peer_ptr(wEx + og, dl), arr_to_f4(exB)); __stcg(peer_ptr(wEy + og, dl), arr_to_f4(eyB));
-              __stcg(peer_ptr(wEz + og, dl), arr_to_f4(ezB));
-              if (has_psi) {
-                __stcg(peer_ptr(wPx + (pP + gp_hi), dl), arr_to_f4(psxB));
-                __stcg(peer_ptr(wPy + (pP + gp_hi), dl), arr_to_f4(psyB));
-              }
-            }
-            if (push_lo_B) {                         // -> the low neighbour's high ghost column
-              const unsigned og = vP + gv_lo;
-              __stcg(peer_ptr(wEx + og, peers.delta_lo), arr_to_f4(exB));
-              __stcg(peer_ptr(wEz + og, peers.delta_lo), arr_to_f4(ezB));
-            }
-          }
           if (oi >= 0) write_snapshot<VW>(g, p.out, oi, P, yB, q, exB, eyB, ezB, p.proj);
         }
         // every store of sweep indices <= i has been issued by this warp
         __syncwarp();
-        // (slab edges: the peer stores above are ordered before the mirror counter by the service
-        // warp's st.release.sys; a system-scope fence here, in every warp and plane of an edge tile,
-        // took a 4096 x 512 x 128 slab from 69 to 31 Gcell/s)
         if (lane == 0) {
           __threadfence_block();
           st_vol_s(&ctl.wdone[w], base_mine + (unsigned)i);
@@ -823,6 +854,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   if (stages_req > 0 && stages_req <= capacity / ntiles) stages = stages_req;
   if (stages > g.tt) stages = g.tt > 0 ? g.tt : 1;
   if (stages > g.X) stages = g.X;
+  if (slab && stages > kSlabMaxStages) stages = kSlabMaxStages;   // (the courier's counter table)
   cfg->stages = stages;
   cfg->l2_window_bytes = (long long)stages * lag * plane_bytes;
   return true;
@@ -839,14 +871,12 @@ inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& c
   Ptrs<float> pp = p;
   SystolicCfg cc = cfg;
   SlabPeers sp;
-  sp.delta_lo = 0; sp.delta_hi = 0; sp.enabled = 0; sp.chunk = kSlabChunk; sp.diag = 0;
+  sp.delta_lo = 0; sp.delta_hi = 0; sp.enabled = 0; sp.edge_lead = 0; sp.diag = 0;
   if (slab) {
     sp = *peers;
-    sp.chunk = kSlabChunk;
-    if (const char* e = getenv("B200FDTD_SLAB_CHUNK")) sp.chunk = atoi(e) < 1 ? 1 : atoi(e);
-    // a consumer may see an edge counter up to chunk - 1 planes late: keep the throttle wider
-    if (sp.chunk + 6 > cc.max_lead) cc.max_lead = sp.chunk + 6;
     sp.diag = 0;
+    sp.edge_lead = 8;
+    if (const char* e = getenv("B200FDTD_SLAB_EDGE_LEAD")) sp.edge_lead = atoi(e) < 0 ? 0 : atoi(e);
     if (const char* e = getenv("B200FDTD_SLAB_DIAG")) sp.diag = atoi(e) & 4;
   }
   void* args[] = {&gg, &pp, &cc, &sync, &sp};   // (cc, sp finalised above)

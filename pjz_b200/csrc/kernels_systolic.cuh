@@ -87,11 +87,12 @@ __device__ __forceinline__ bool wait_ge(const unsigned* flag, unsigned need, uns
   }
 }
 
-// Progress counters [stages][ntiles], the status word, then 2 x stages MIRROR slots: in a y-slab
-// session the neighbouring GPUs store the counters of their edge tiles there (low neighbour's
-// last tile, then high neighbour's first tile) -- see kernels_lean.cuh, SlabPeers.
+// Progress counters [stages][ntiles], the status word, then 4 x stages slots of a y-slab session
+// (kernels_lean.cuh, SlabPeers): MIRROR slots, where the neighbouring GPUs' couriers store the
+// counters of their edge tiles (low neighbour's last tile, then high neighbour's first tile),
+// and this GPU's COURIER progress (low side, then high side).
 inline size_t systolic_sync_bytes(const SystolicCfg& c) {
-  return ((size_t)c.stages * c.ntiles + 1 + 2 * (size_t)c.stages) * kSysFlagStride * sizeof(unsigned);
+  return ((size_t)c.stages * c.ntiles + 1 + 4 * (size_t)c.stages) * kSysFlagStride * sizeof(unsigned);
 }
 
 template <typename T>
