@@ -289,11 +289,11 @@ int b200fdtd_session_layout2(const b200fdtd_session* session, int64_t* info);
  * Domain decomposition along y for one process per GPU (pjz_b200/_decomp.py:P2PSlabRun; there is
  * no reference counterpart).  The local domain of `desc` has Y = owned columns + 2: the tiles of
  * the persistent kernel cover the owned columns [ylo, yhi) = [1, Y-1) and the columns 0 and Y-1 are
- * ghosts that the NEIGHBOURING GPUs fill: every time step, the warp that owns a slab's edge column
- * stores its new fields also into the neighbour's ghost column (peer-mapped stores over NVLink)
- * and the edge tile's progress counter into the neighbour's mirror slot (st.release.sys), so the
- * neighbour's edge tiles depend on them exactly as on a local tile.  One launch advances any
- * number of steps; nothing is exchanged by the host.  Requirements: fp32 storage, 125 <= Z <= 128
+ * ghosts that the NEIGHBOURING GPUs fill: a courier CTA of every launch copies each newly
+ * finished plane of the slab's edge columns into the neighbour's ghost column (peer-mapped stores
+ * over NVLink) and then the edge tile's progress counter into the neighbour's mirror slot
+ * (st.release.sys), so the neighbour's edge tiles depend on them exactly as on a local tile.  One
+ * launch advances any number of steps; nothing is exchanged by the host.  Requirements: fp32 storage, 125 <= Z <= 128
  * (the warp-per-column-pair kernel); every rank uses the same local shape and launch parameters;
  * every workspace is mapped into its two neighbours' address space (CUDA IPC or a VMM export --
  * the caller's business; pass the local base for a neighbour that is this rank itself).

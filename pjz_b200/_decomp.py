@@ -593,10 +593,10 @@ def fdtdz_decomposed_y(epsilon, dt, source_field, source_waveform, source_positi
 #
 # The ghost-zone scheme above pays (Yo + 2G) / Yo redundant work, one host-driven NCCL round per G
 # steps and a pipeline fill/drain per launch.  Here every rank keeps ONE ghost column per side and
-# the persistent kernel itself does the exchange (include/b200fdtd.h, "y-slab sessions"): the warp
-# that owns a slab's edge column stores its new fields into the neighbour's ghost column through
-# peer-mapped memory, the edge tile's progress counter goes into the neighbour's mirror slot, and
-# the neighbour's edge tiles wait on it like on any local tile.  The whole run is one launch per
+# the persistent launch itself does the exchange (include/b200fdtd.h, "y-slab sessions"): a courier
+# CTA copies each newly finished plane of the slab's edge columns into the neighbour's ghost column
+# through peer-mapped memory, then the edge tile's progress counter into the neighbour's mirror
+# slot, and the neighbour's edge tiles wait on it like on any local tile.  The whole run is one launch per
 # GPU; transfers overlap the interior update tile by tile; no redundant cells.  Bit-identical to the
 # single-GPU run by construction (every owned cell sees the same operands in the same order).
 

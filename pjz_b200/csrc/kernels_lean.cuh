@@ -138,7 +138,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   unsigned* const cour_lo = mirror_hi + (size_t)S * kSysFlagStride;     // [S]: courier progress, low side
   unsigned* const cour_hi = cour_lo + (size_t)S * kSysFlagStride;       // ... high side
   const bool edge_lo = SLAB && t == 0, edge_hi = SLAB && t == NT - 1;
-  // A neighbour GPU's counter arrives ~6 us (two planes) later than a local tile's, so the tiles
+  // A neighbour GPU's counter arrives ~6-9 us (three planes) later than a local tile's, so the tiles
   // an edge's delay reaches within one round (one tile further per stage) may run further ahead of
   // their successor stage before they are throttled; the L2 window grows for those tiles only.
   const int max_lead = cfg.max_lead + ((SLAB && (t < S || t >= NT - S)) ? peers.edge_lead : 0);
@@ -875,7 +875,9 @@ inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& c
   if (slab) {
     sp = *peers;
     sp.diag = 0;
-    sp.edge_lead = 8;
+    // 2 GPUs, 4096 x 512 x 128 per GPU, Gcell/s (wrapped single-GPU slab: 84-85 from 8 upwards):
+    // 0: 110, 8: 156, 12: 161, 16: 165, 24: 168 -- NVLink adds ~3 us to the counter's flight
+    sp.edge_lead = 24;
     if (const char* e = getenv("B200FDTD_SLAB_EDGE_LEAD")) sp.edge_lead = atoi(e) < 0 ? 0 : atoi(e);
     if (const char* e = getenv("B200FDTD_SLAB_DIAG")) sp.diag = atoi(e) & 4;
   }
