@@ -56,6 +56,55 @@ def main():
                       "rel_l2_vs_reference_formula": err}))
     del fields
     torch.cuda.empty_cache()
+  # ---- a4 / f1: one-pass projection and fused overlaps -----------------------------------------------
+  from pjz_b200 import fdtdz_jax
+  for ww, shape in [(4, (448, 448, 96)), (1, (192, 192, 96)), (8, (192, 192, 96))]:
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n_out = 2 * ww + 1
+    snaps = torch.randn((n_out, 3) + shape, generator=g, device="cuda")
+    Wm = torch.randn((2 * ww, n_out), generator=g, device="cuda")
+    Wn = Wm.cpu().numpy()
+    nvox = 3 * shape[0] * shape[1] * shape[2]
+    ms = ev_time(lambda: fdtdz_jax.project(snaps, Wn))
+
+    def ref():
+      o = torch.einsum("ij,j...->i...", Wm, snaps)
+      return torch.complex(o[:ww], o[ww:])
+    ms_ref = ev_time(ref, reps=3)
+    want = ref()
+    err = float((fdtdz_jax.project(snaps, Wn) - want).abs().max() / want.abs().max())
+    bytes_alg = nvox * (n_out * 4 + ww * 8)
+    print(json.dumps({"row": "a4/f1 one-pass snapshot projection (b200fdtd_project)", "ww": ww,
+                      "snapshots": n_out, "volume": shape, "ms": ms, "ms_torch_einsum_plus_complex": ms_ref,
+                      "speedup": ms_ref / ms,
+                      "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": peak,
+                                   "unit": "GB/s", "frac": bytes_alg / ms / 1e6 / peak},
+                      "max_abs_err_over_max": err}))
+    del snaps, want
+    torch.cuda.empty_cache()
+  for nports in (2, 8):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ww, shape = 4, (448, 448, 96)
+    if nports == 8:
+      ww, shape = 1, (320, 192, 96)
+    fields = [torch.view_as_complex(torch.randn((ww, 3) + shape + (2,), generator=g, device="cuda"))
+              for _ in range(nports)]
+    modes = [torch.randn((ww, 2, 1, shape[1], shape[2]), generator=g, device="cuda") for _ in range(nports)]
+    betas = [np.full(ww, 0.33) for _ in range(nports)]
+    pos = [6 + i for i in range(nports)]
+    fwd = [i % 2 == 0 for i in range(nports)]
+    ms = ev_time(lambda: glue._overlaps_fused(fields, modes, betas, pos, fwd))
+
+    def ref_ov():
+      amps = [glue._overlap(m, b, p, f, fl)[:, 0] for fl, m, b, p, f in zip(fields, modes, betas, pos, fwd)]
+      return [[glue._overlap(m, b, p, f, fl)[:, 1] / a for m, b, p, f in zip(modes, betas, pos, fwd)]
+              for a, fl in zip(amps, fields)]
+    ms_ref = ev_time(ref_ov, reps=2)
+    print(json.dumps({"row": "f1 port overlaps, all pairs in one launch (b200fdtd_overlaps)",
+                      "nports": nports, "ww": ww, "volume": shape, "ms": ms,
+                      "ms_eager_per_port_chains": ms_ref, "speedup": ms_ref / ms}))
+    del fields
+    torch.cuda.empty_cache()
   # ---- f3 ------------------------------------------------------------------------------------------
   from pjz_b200 import mode
   from pjz_b200._mode_gpu import mode_gpu
