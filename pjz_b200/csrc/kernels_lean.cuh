@@ -108,11 +108,8 @@ __device__ __forceinline__ float4 arr_to_f4(const float (&v)[4]) {
 
 // STATS = per-warp wait-time accounting printed at the end (debug builds of the plan only).
 // SLAB = y-slab session: tiles cover [g.ylo, g.yhi), edge tiles exchange with the neighbour GPUs.
-// CW = compute warps the build is sized for: 8 (+ service warp = 9 warps: three on one SM
-// sub-partition, at most 168 registers per thread) or 7 (8 warps, two per sub-partition: up to 255
-// registers, ~17 % fewer executed instructions because loop-invariant values stay in registers).
-template <bool STATS, bool SLAB, int CW>
-__global__ void __launch_bounds__(32 * (CW + 1), 1)
+template <bool STATS, bool SLAB>
+__global__ void __launch_bounds__(32 * (kLeanMaxWarps + 1), 1)
 lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* sync,
             const SlabPeers peers) {
   constexpr int VW = 4;
@@ -782,17 +779,9 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
 }
 
-inline const void* lean_fn(bool stats, bool slab, int cw) {
-  if (slab) return (const void*)lean_kernel<false, true, 8>;
-  if (stats) return (const void*)lean_kernel<true, false, 8>;
-  return cw == 7 ? (const void*)lean_kernel<false, false, 7> : (const void*)lean_kernel<false, false, 8>;
-}
-
-// Compute warps per CTA: B200FDTD_LEAN_WARPS = 7 | 8 (slab sessions and the accounting build: 8).
-inline int lean_compute_warps(bool slab) {
-  if (slab || getenv("B200FDTD_LEAN_STATS") != nullptr) return 8;
-  if (const char* e = getenv("B200FDTD_LEAN_WARPS")) return atoi(e) == 7 ? 7 : 8;
-  return 8;
+inline const void* lean_fn(bool stats, bool slab) {
+  if (slab) return (const void*)lean_kernel<false, true>;
+  return stats ? (const void*)lean_kernel<true, false> : (const void*)lean_kernel<false, false>;
 }
 
 // Compute warps for a tile of `tile_y` owned columns: columns 0 .. tile_y form H, two per warp.
@@ -810,8 +799,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   if (reduced) { *why = "fp32 storage only"; return false; }
   if (g.Zq != 32) { *why = "needs a z-column of exactly 32 vectors (125 <= Z <= 128)"; return false; }
   if (g.N / 4 * 3 >= (1ll << 32)) { *why = "domain too large for 32-bit vector indices"; return false; }
-  const int cw = lean_compute_warps(g.yhi - g.ylo != g.Y);
-  int max_tile = 2 * cw - 1;                     // 2*NW - 1 owned columns fill NW warps exactly
+  int max_tile = 2 * kLeanMaxWarps - 1;          // 2*NW - 1 owned columns fill NW warps exactly
   while (max_tile >= 1 && lean_smem_bytes(g, max_tile) + 256 > 227 * 1024) --max_tile;
   if (max_tile < 1) { *why = "staging ring does not fit in shared memory"; return false; }
   if (tile_y_req > 0 && tile_y_req < max_tile) max_tile = tile_y_req;
@@ -844,9 +832,9 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   cfg->trap_on_timeout = 1;
   int occ = 0;
   cfg->need_zfix = 0;
-  cfg->unroll = cw;                              // (field reused: compute warps the build is sized for)
+  cfg->unroll = 1;
   const bool slab = Yspan != g.Y;
-  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab, cw);
+  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
           cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, cfg->threads, cfg->smem_bytes) !=
@@ -875,7 +863,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
 inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& cfg, unsigned* sync,
                        cudaStream_t st, const SlabPeers* peers = nullptr) {
   const bool slab = peers != nullptr && peers->enabled;
-  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab, cfg.unroll);
+  const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        cfg.smem_bytes);
   if (e != cudaSuccess) return (int)e;
