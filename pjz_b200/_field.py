@@ -354,15 +354,21 @@ def _overlaps_fused(fields, modes, betas, pos, is_fwd):
         if tuple(m.shape[-3:]).count(1) == 1 else m
     flat.append(m)
   vals = fdtdz_jax.overlaps(fields, flat, axes, [g[0] for g in geo])   # (F, M, 2, ww)
-  coefs = [[_amplitudes(g[2], vals[f, m].transpose(0, 1), g[1]) for m, g in enumerate(geo)]
-           for f in range(len(fields))]                                # each (ww, 2): in, out
+  # the 2x2 least-squares fits of `_amplitudes` (:293-302) for all pairs at once: one pinv stack
+  # per port on the host, one einsum on the device
+  pinvs = []
+  for _, x, beta in geo:
+    a = np.stack([np.exp(-1j * beta[:, None] * x), np.exp(1j * beta[:, None] * x)], axis=1)
+    pinvs.append(np.linalg.pinv(a))                                    # (ww, plane j, coefficient i)
+  w = torch.from_numpy(np.stack(pinvs).astype(np.complex64)).to(dev)  # (M, ww, j, i)
+  coefs = torch.einsum("mwji,fmjw->fmwi", w, vals)                     # (F, M, ww, 2): in, out
   amplitudes = []
   for i, fwd in enumerate(is_fwd):
     if fwd is None:
       amplitudes.append(torch.ones(vals.shape[-1], dtype=torch.complex64, device=dev))
     else:
-      amplitudes.append(coefs[i][i][:, 0])
-  svals = [[coefs[f][m][:, 1] / amplitudes[f] for m in range(len(modes))]
+      amplitudes.append(coefs[i, i, :, 0])
+  svals = [[coefs[f, m, :, 1] / amplitudes[f] for m in range(len(modes))]
            for f in range(len(fields))]
   return amplitudes, svals
 
