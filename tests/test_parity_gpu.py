@@ -5,7 +5,8 @@ Bar (BASELINE.json north_star): relative L2 <= 1e-5 in fp32 mode against the flo
 also demand BIT-EXACT equality with the C fp32 oracle, whose per-cell operation order the
 kernels share (oracle/fdtd_c.c, pjz_b200/csrc/fdtd_common.cuh).  Reduced precision (fp16
 storage): bit-exact against the C oracle's fp16-storage mode and rel-L2 <= 5e-3 against the
-fp32 run.  At BASELINE sizes, where the oracle is too slow, size-independent properties are
+fp32 run on these short runs (the stated bound of the mode, 2e-2 for runs of up to 20 000 steps, is
+measured in tests/test_parity_configs_gpu.py).  At BASELINE sizes, where the oracle is too slow, size-independent properties are
 used: the two independent kernels agree bit-for-bit, linearity in the source, schedule
 selection.
 """
@@ -246,7 +247,7 @@ def test_reduced_precision(axis, kernel):
   out = run_gpu(kw, kernel=kernel)
   np.testing.assert_array_equal(out, fdtd_c.fdtdz(**kw))
   full = fdtd_numpy.fdtdz(**{**kw, "use_reduced_precision": False})
-  assert rel_l2(out, full) <= 5e-3     # stated bound for the reduced-precision mode
+  assert rel_l2(out, full) <= 5e-3     # 50 steps; long runs: tests/test_parity_configs_gpu.py
 
 
 def test_host_path_equals_device_path():
