@@ -531,9 +531,13 @@ class YSlabRun:
     slab, G, group, world = self.slab, self.G, self.group, self.world
     right, left = self._peer(self.rank + 1), self._peer(self.rank - 1)
     Yl = self.nloc + 2 * G
+    timing = getattr(self, "time_exchange", False) and torch.cuda.is_available()
+    marks = []
     for n0 in range(0, self.tt, max(G, 1)):
       st = slab.state(n0)
       if n0 > 0:                                             # (the initial state is all zero)
+        if timing:
+          a = torch.cuda.Event(enable_timing=True); a.record()
         send_lo = _pack(st, G, 2 * G)                        # my low owned edge
         send_hi = _pack(st, Yl - 2 * G, Yl - G)              # my high owned edge
         recv_hi, recv_lo = torch.empty_like(send_lo), torch.empty_like(send_hi)
@@ -541,7 +545,13 @@ class YSlabRun:
         _exchange(send_hi, recv_lo, right, left, group, world)   # -> right's low ghost
         _unpack(recv_hi, st, Yl - G, Yl)
         _unpack(recv_lo, st, 0, G)
+        if timing:
+          b = torch.cuda.Event(enable_timing=True); b.record()
+          marks.append((a, b))
       slab.advance(n0, min(G, self.tt - n0))
+    if timing:
+      torch.cuda.synchronize()
+      self.exchange_ms = sum(a.elapsed_time(b) for a, b in marks)   # pack + send/recv + unpack
 
   def local_snapshots(self):
     snaps = self.slab.snapshots()                            # (n_out, 3, xx, nloc+2G, zz)

@@ -498,7 +498,9 @@ def test_field_fused_projection_on_the_gpu():
 # ---- adjoint product-reduce ----------------------------------------------------
 
 @pytest.mark.parametrize("nports,ww,shape", [(1, 1, (5, 4, 3)), (2, 3, (9, 8, 7)), (4, 2, (16, 12, 10)),
-                                             (8, 4, (20, 16, 12)), (16, 1, (6, 5, 4))])
+                                             (8, 4, (20, 16, 12)), (16, 1, (6, 5, 4)),
+                                             # > 48 KB of coefficient table in shared memory
+                                             (16, 26, (3, 2, 2)), (12, 64, (2, 2, 2))])
 def test_adjoint_reduce_matches_the_reference_formula(nports, ww, shape):
   """b200fdtd_adjoint_reduce vs the mirror of pjz's N^2-temporaries formula
   (_field.py:380-398 -> pjz_b200/_field.py:_scatter_bwd), float32 tolerance 1e-5."""
