@@ -48,6 +48,7 @@ constexpr int kLeanXR = 2;             // depth of the boundary-H exchange ring
 constexpr int kLeanERows = 8;          // 512-byte rows per E slot   (3 slots: P, P+1, in flight)
 constexpr int kLeanHRows = 12;         // 512-byte rows per H/B slot (2 slots: P, in flight)
 constexpr int kSlabMaxStages = 36;     // y-slab sessions: most pipeline stages (courier counter table)
+constexpr int kSlabCouriers = 8;       // y-slab sessions: courier CTAs (SMs kept free of tiles)
 
 struct LeanCtl {
   unsigned avail;      // min over the three predecessor counters (raw, cumulative)
@@ -149,8 +150,8 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   __syncthreads();
 
   // ==================================== courier CTA ===============================================
-  // Slab sessions: one extra CTA (block index S*NT, on an SM no tile uses) carries the halo to the
-  // neighbour GPUs.  One warp per edge counter (side x stage): it watches the counter the edge
+  // Slab sessions: up to eight extra CTAs (block indices >= S*NT, on SMs no tile uses) carry the halo
+  // to the neighbour GPUs.  One warp per edge counter (side x stage): it watches the counter the edge
   // tile publishes (ld.acquire.gpu), copies the planes that counter newly covers -- the slab's
   // last owned column (E, H, psiH) into the HIGH neighbour's low ghost column, the first owned
   // column (Ex, Ez) into the LOW neighbour's high ghost column, read from the local L2, stored
@@ -163,9 +164,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   // counters forwarded from here), and peer stores issued by a compute warp throttle that warp
   // across NVLink (two GPUs: 80 Gcell/s per GPU against 106 wrapped).  Here both sit on an idle SM
   // and only add latency, which the pipeline's slack (max_lead) absorbs.
-  if (SLAB && blockIdx.x == (unsigned)(S * NT)) {
+  if (SLAB && blockIdx.x >= (unsigned)(S * NT)) {
     __shared__ unsigned cour_last[2 * kSlabMaxStages];       // count already carried, per counter
     const int nwarps = (int)(blockDim.x >> 5), wid = tid >> 5;
+    const int NC = (int)gridDim.x - S * NT, ci = (int)blockIdx.x - S * NT;   // courier CTAs, mine
     for (int c = tid; c < 2 * S; c += (int)blockDim.x) cour_last[c] = 0u;
     __syncthreads();
     const unsigned PVn = (unsigned)Y * ZQ, PPn = (unsigned)Y * g.npg;
@@ -174,7 +176,10 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
     bool busy = true, give_up = false;
     while (busy && !give_up) {
       busy = false;
-      for (int c = wid; c < 2 * S; c += nwarps) {            // counter c = side * S + stage
+      // counter c = side * S + stage; dealt across the courier CTAs first (a system-scope fence
+      // waits for every peer store in flight on its SM, whoever issued it: 8 GPUs, all counters on
+      // one SM: 34-43 k cycles per push on some ranks against 12 k with two GPUs), then across warps
+      for (int c = ci + wid * NC; c < 2 * S; c += nwarps * NC) {
         const unsigned last_c = cour_last[c];
         const int side = c / S, jj = c % S;
         const int left = g.tt - g.n0 - jj;                   // steps n0+jj, n0+jj+S, ... < tt
@@ -843,7 +848,8 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
     *why = "kernel does not fit on an SM";
     return false;
   }
-  const long long capacity = (long long)occ * sms - (slab ? 1 : 0);   // (a slab's courier CTA)
+  // a slab's courier CTAs: up to kSlabCouriers SMs are kept free of tiles
+  const long long capacity = (long long)occ * sms - (slab ? (sms >= 64 ? kSlabCouriers : 1) : 0);
   if (ntiles > capacity) { *why = "more y-tiles than co-resident CTAs"; return false; }
   int stages = (int)(capacity / ntiles);
   const long long plane_bytes = g.P * 4ll * 15;
@@ -882,7 +888,15 @@ inline int lean_launch(const Geom& g, const Ptrs<float>& p, const SystolicCfg& c
     if (const char* e = getenv("B200FDTD_SLAB_DIAG")) sp.diag = atoi(e) & 4;
   }
   void* args[] = {&gg, &pp, &cc, &sync, &sp};   // (cc, sp finalised above)
-  e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles + (slab ? 1 : 0)), dim3(cfg.threads),
+  int couriers = 0;
+  if (slab) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    couriers = sms >= 64 ? kSlabCouriers : 1;
+    if (couriers > 2 * cfg.stages) couriers = 2 * cfg.stages;
+  }
+  e = cudaLaunchCooperativeKernel(fn, dim3(cfg.stages * cfg.ntiles + couriers), dim3(cfg.threads),
                                   args, cfg.smem_bytes, st);
   if (e != cudaSuccess) return (int)e;
   systolic_check_kernel<<<1, 1, 0, st>>>(sync + (size_t)cfg.stages * cfg.ntiles * kSysFlagStride);
