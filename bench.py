@@ -475,6 +475,21 @@ def main():
   assert np.isfinite(checksum) and checksum > 0, "engine produced an empty/non-finite field"
   value = world * cells * tt * args.steps / (ms / 1e3) / 1e9
 
+  # ---- this box: device copy bandwidth, the way MEASURED_PEAKS.json's hbm_gbs was taken (the pool is
+  # bimodal for the fp32 flagship; this says what kind of box the line comes from)
+  box = None
+  if rank == 0:
+    src_t = torch.empty(1 << 29, dtype=torch.bfloat16, device="cuda")
+    dst_t = torch.empty_like(src_t)
+    best = 0.0
+    for _ in range(6):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record(); dst_t.copy_(src_t); b.record()
+      torch.cuda.synchronize()
+      best = max(best, 2 * src_t.numel() * 2 / (a.elapsed_time(b) / 1e3) / 1e9)
+    box = {"copy_gbs_now": best, "how": "torch b.copy_(a) over 512 Mi bf16 elements, best of 6"}
+    del src_t, dst_t
+
   # ---- e2e: HOST pinned buffers through the public call (copies inside the timed region) ----
   e2e = None
   if not args.no_e2e:
@@ -594,7 +609,7 @@ def main():
                          "inputs larger than L2, no flush needed")),
                  "plan": info},
       "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-      "clocks": clocks, "reduced_precision": reduced, "decomp": decomp,
+      "clocks": clocks, "box": box, "reduced_precision": reduced, "decomp": decomp,
   }
   print(json.dumps(line))
   if world > 1:
