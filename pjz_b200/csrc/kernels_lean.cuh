@@ -392,7 +392,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
     unsigned long long t0 = 0;
-    unsigned spins = 0, ns = 20;
+    unsigned spins = 0, ns = (unsigned)cfg.need_zfix;   // (field reused by the lean kernels: first back-off, ns)
     while (true) {
       __nanosleep(ns);
       if (__all_sync(0xffffffffu, cond())) return true;
@@ -774,11 +774,16 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   cp_async_wait<0>();
   __syncwarp();
   if constexpr (STATS) {
-    if (lane == 0 && (t == 0 || t == NT / 2)) {
+    // every CTA, first and last warp: where the warp's time went, and on which SM (a CTA that never
+    // waits is what the others wait for)
+    if (lane == 0 && (w == 0 || w == NWt - 1)) {
       const double tot = (double)(clock64() - st_begin);
-      printf("leanstats j %d t %d w %d iters %u cyc/iter %.0f  cp %.3f avail %.3f next %.3f rcnt %.3f hcnt %.3f\n",
-             j, t, w, kk, tot / (kk ? kk : 1), st_cp / tot, st_avail / tot, st_next / tot,
-             st_rc / tot, st_hc / tot);
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const double waits = (double)(st_cp + st_avail + st_next + st_rc + st_hc);
+      printf("leanstats j %d t %d w %d sm %u iters %u cyc/iter %.0f busy/iter %.0f  cp %.3f avail %.3f next %.3f rcnt %.3f hcnt %.3f\n",
+             j, t, w, smid, kk, tot / (kk ? kk : 1), (tot - waits) / (kk ? kk : 1), st_cp / tot,
+             st_avail / tot, st_next / tot, st_rc / tot, st_hc / tot);
     }
   }
   if (lane == 0) atomicAdd(&ctl.exited, 1u);
@@ -825,7 +830,7 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   // the HBM latency, and the prefetches compete with them for L2 bandwidth and power.
   cfg->pf_ahead = 0;
   cfg->svc_sleep_ns = 200;
-  cfg->spin_ns_max = 160;
+  cfg->spin_ns_max = 400;
   cfg->discard = 1;
   if (const char* e = getenv("B200FDTD_LEAN_DISCARD")) cfg->discard = atoi(e);
   if (const char* e = getenv("B200FDTD_SPIN_NS")) cfg->spin_ns_max = atoi(e);
@@ -836,7 +841,10 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
   int occ = 0;
-  cfg->need_zfix = 0;
+  // back-off of a waiting warp: first sleep 200 ns, doubling up to 400 (round 2: 20 -> 160 before;
+  // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
+  cfg->need_zfix = 200;
+  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
   cfg->unroll = 1;
   const bool slab = Yspan != g.Y;
   const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);

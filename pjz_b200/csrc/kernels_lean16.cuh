@@ -245,7 +245,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
     unsigned long long t0 = 0;
-    unsigned spins = 0, ns = 20;
+    unsigned spins = 0, ns = (unsigned)cfg.need_zfix;   // (field reused by the lean kernels: first back-off, ns)
     while (true) {
       __nanosleep(ns);
       if (__all_sync(0xffffffffu, cond())) return true;
@@ -646,7 +646,7 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   cfg->max_lead = 10;
   cfg->pf_ahead = 0;                             // see lean_configure: 126.2 vs 122.2 Gcell/s (fp16 cfg2)
   cfg->svc_sleep_ns = 200;
-  cfg->spin_ns_max = 160;
+  cfg->spin_ns_max = 400;
   // L2 discard of consumed lines: off by default here.  With these short columns (and half the
   // bytes per cell in fp16) HBM is nowhere near its limit, and the CCTL instructions cost 4-5 %
   // (256x256x128 fp16: 106.3 vs 102.4 Gcell/s; fp32 Z=64: 80.1 vs 76.3).  B200FDTD_LEAN_DISCARD=1
@@ -660,7 +660,10 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   if (cfg->max_lead < 6) cfg->max_lead = 6;
   if (cfg->pf_ahead < 0) cfg->pf_ahead = 0;
   cfg->trap_on_timeout = 1;
-  cfg->need_zfix = 0;
+  // back-off of a waiting warp: first sleep 200 ns, doubling up to 400 (round 2: 20 -> 160 before;
+  // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
+  cfg->need_zfix = 200;
+  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
   cfg->unroll = 1;
   int occ = 0;
   const void* fn = lean16_fn<T, LPC>();
