@@ -547,7 +547,13 @@ def main():
   if not args.no_decomp:
     del out, dev
     torch.cuda.empty_cache()
-    decomp = run_decomp(args, rank, world, local)
+    if world == 1:
+      try:                                         # the headline must not be lost to this record
+        decomp = run_decomp(args, rank, world, local)
+      except Exception as e:                       # noqa: BLE001
+        decomp = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    else:                                          # (collective: a rank cannot fail alone)
+      decomp = run_decomp(args, rank, world, local)
 
   if rank != 0:
     if world > 1:
