@@ -5,7 +5,7 @@ Bar (BASELINE.json north_star): relative L2 <= 1e-5 in fp32 mode against the flo
 also demand BIT-EXACT equality with the C fp32 oracle, whose per-cell operation order the
 kernels share (oracle/fdtd_c.c, pjz_b200/csrc/fdtd_common.cuh).  Reduced precision (fp16
 storage): bit-exact against the C oracle's fp16-storage mode and rel-L2 <= 5e-3 against the
-fp32 run on these short runs (the stated bound of the mode, 2e-2 for runs of up to 20 000 steps, is
+fp32 run on these short runs (the stated bound of the mode, 3e-2 for runs of up to 20 000 steps, is
 measured in tests/test_parity_configs_gpu.py).  At BASELINE sizes, where the oracle is too slow, size-independent properties are
 used: the two independent kernels agree bit-for-bit, linearity in the source, schedule
 selection.
