@@ -54,6 +54,7 @@ def parse():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  ap.add_argument("--no-ab", action="store_true", help="skip the same-box A/B of the L2 prefetch setting")
   ap.add_argument("--no-reduced", action="store_true",
                   help="skip the reduced-precision sub-record")
   ap.add_argument("--no-decomp", action="store_true",
@@ -522,6 +523,39 @@ def main():
     box = {"copy_gbs_now": best, "how": "torch b.copy_(a) over 512 Mi bf16 elements, best of 6"}
     del src_t, dst_t
 
+  # ---- same-box reference: the one setting round 2 changed in the flagship kernel's plan (the L2
+  # prefetch of the service warp, 6 planes ahead in round 1, off now), both ways on a 4 000-step cut
+  # of the same workload -- the pool's boxes differ by 25 % on this kernel, so a
+  # number from another box says little
+  same_box = None
+  if rank == 0 and not args.no_ab and args.workload == "bend" and not args.reduced:
+    try:
+      short = dict(dev)
+      short["source_waveform"] = dev["source_waveform"][:4000].contiguous()
+      short["output_steps"] = (3997, 4000, 1)
+      res_ab = {}
+      for label, pf in (("l2_prefetch_off_this_build", None), ("l2_prefetch_6_planes_round1_setting", "6")):
+        old_pf = os.environ.pop("B200FDTD_PF_AHEAD", None)
+        if pf is not None:
+          os.environ["B200FDTD_PF_AHEAD"] = pf
+        try:
+          fdtdz_jax.fdtdz(**short)
+          torch.cuda.synchronize()
+          a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          a.record()
+          for _ in range(3):
+            fdtdz_jax.fdtdz(**short)
+          b.record()
+          torch.cuda.synchronize()
+          res_ab[label] = cells * 4000 * 3 / (a.elapsed_time(b) / 1e3) / 1e9
+        finally:
+          os.environ.pop("B200FDTD_PF_AHEAD", None)
+          if old_pf is not None:
+            os.environ["B200FDTD_PF_AHEAD"] = old_pf
+      same_box = dict(res_ab, unit=UNIT, workload="first 4000 steps of the same workload, 3 calls each")
+    except Exception as e:                                   # noqa: BLE001
+      same_box = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
   # ---- e2e: HOST pinned buffers through the public call (copies inside the timed region) ----
   e2e = None
   if not args.no_e2e:
@@ -625,7 +659,7 @@ def main():
                          "inputs larger than L2, no flush needed")),
                  "plan": info},
       "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-      "clocks": clocks, "box": box, "reduced_precision": reduced, "decomp": decomp,
+      "clocks": clocks, "box": box, "same_box_ab": same_box, "reduced_precision": reduced, "decomp": decomp,
   }
   print(json.dumps(line))
   if world > 1:
