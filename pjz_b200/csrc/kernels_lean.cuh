@@ -121,7 +121,12 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
   const int S = cfg.stages, NT = cfg.ntiles;
-  const int t = blockIdx.x % NT, j = blockIdx.x / NT;
+  // block index -> (stage, tile): stage-major (consecutive blocks = the stages of one tile; round 2:
+  // cfg2 95.8 -> 97.5 Gcell/s, cfg3 94.3 -> 96.0, cfg4 unchanged, 4096 x 512 slab 86.8 -> 89.9, the
+  // board draws a little less power) or tile-major (B200FDTD_LEAN_MAP=0: round 1's order)
+  const bool stage_major = cfg.unroll == 2 && blockIdx.x < (unsigned)(S * NT);
+  const int t = stage_major ? (int)blockIdx.x / S : (int)(blockIdx.x % NT);
+  const int j = stage_major ? (int)blockIdx.x % S : (int)(blockIdx.x / NT);
   const int ybase = SLAB ? g.ylo : 0, yspan = SLAB ? g.yhi - g.ylo : g.Y;
   const int y0 = ybase + (int)((long long)t * yspan / NT);
   const int Yt = ybase + (int)((long long)(t + 1) * yspan / NT) - y0;
@@ -845,7 +850,8 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
   cfg->need_zfix = 200;
   if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
-  cfg->unroll = 1;
+  cfg->unroll = 2;                               // (field reused: 2 = stage-major block order, 1 = tile-major)
+  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->unroll = atoi(e) != 0 ? 2 : 1;
   const bool slab = Yspan != g.Y;
   const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=

@@ -68,7 +68,9 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
   const int S = cfg.stages, NT = cfg.ntiles;
-  const int t = blockIdx.x % NT, j = blockIdx.x / NT;
+  const bool stage_major = cfg.unroll == 2;        // block order, see kernels_lean.cuh
+  const int t = stage_major ? (int)blockIdx.x / S : (int)(blockIdx.x % NT);
+  const int j = stage_major ? (int)blockIdx.x % S : (int)(blockIdx.x / NT);
   const int y0 = (int)((long long)t * g.Y / NT);
   const int Yt = (int)((long long)(t + 1) * g.Y / NT) - y0;
   const int X = g.X, Y = g.Y, Zq = g.Zq, npg = g.npg;
@@ -664,7 +666,8 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
   cfg->need_zfix = 200;
   if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
-  cfg->unroll = 1;
+  cfg->unroll = 2;                               // (field reused: block order, 2 = stage-major; fp16 cfg2 130.7 -> 131.1)
+  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->unroll = atoi(e) != 0 ? 2 : 1;
   int occ = 0;
   const void* fn = lean16_fn<T, LPC>();
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=
