@@ -124,7 +124,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   // block index -> (stage, tile): stage-major (consecutive blocks = the stages of one tile; round 2:
   // cfg2 95.8 -> 97.5 Gcell/s, cfg3 94.3 -> 96.0, cfg4 unchanged, 4096 x 512 slab 86.8 -> 89.9, the
   // board draws a little less power) or tile-major (B200FDTD_LEAN_MAP=0: round 1's order)
-  const bool stage_major = cfg.unroll == 2 && blockIdx.x < (unsigned)(S * NT);
+  const bool stage_major = cfg.block_order == 2 && blockIdx.x < (unsigned)(S * NT);
   const int t = stage_major ? (int)blockIdx.x / S : (int)(blockIdx.x % NT);
   const int j = stage_major ? (int)blockIdx.x % S : (int)(blockIdx.x / NT);
   const int ybase = SLAB ? g.ylo : 0, yspan = SLAB ? g.yhi - g.ylo : g.Y;
@@ -397,7 +397,7 @@ lean_kernel(const Geom g, const Ptrs<float> p, const SystolicCfg cfg, unsigned* 
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
     unsigned long long t0 = 0;
-    unsigned spins = 0, ns = (unsigned)cfg.need_zfix;   // (field reused by the lean kernels: first back-off, ns)
+    unsigned spins = 0, ns = (unsigned)cfg.spin_ns0;
     while (true) {
       __nanosleep(ns);
       if (__all_sync(0xffffffffu, cond())) return true;
@@ -848,10 +848,10 @@ inline bool lean_configure(const Geom& g, bool reduced, int tile_y_req, int stag
   int occ = 0;
   // back-off of a waiting warp: first sleep 200 ns, doubling up to 400 (round 2: 20 -> 160 before;
   // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
-  cfg->need_zfix = 200;
-  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
-  cfg->unroll = 2;                               // (field reused: 2 = stage-major block order, 1 = tile-major)
-  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->unroll = atoi(e) != 0 ? 2 : 1;
+  cfg->spin_ns0 = 200;
+  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->spin_ns0 = atoi(e) < 1 ? 1 : atoi(e);
+  cfg->block_order = 2;                          // stage-major (tile-major: 1)
+  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->block_order = atoi(e) != 0 ? 2 : 1;
   const bool slab = Yspan != g.Y;
   const void* fn = lean_fn(getenv("B200FDTD_LEAN_STATS") != nullptr, slab);
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=

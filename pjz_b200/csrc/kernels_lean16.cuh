@@ -68,7 +68,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int NW = (int)(blockDim.x >> 5) - 1;       // compute warps
   const int S = cfg.stages, NT = cfg.ntiles;
-  const bool stage_major = cfg.unroll == 2;        // block order, see kernels_lean.cuh
+  const bool stage_major = cfg.block_order == 2;        // block order, see kernels_lean.cuh
   const int t = stage_major ? (int)blockIdx.x / S : (int)(blockIdx.x % NT);
   const int j = stage_major ? (int)blockIdx.x % S : (int)(blockIdx.x / NT);
   const int y0 = (int)((long long)t * g.Y / NT);
@@ -247,7 +247,7 @@ lean16_kernel(const Geom g, const Ptrs<T> p, const SystolicCfg cfg, unsigned* sy
   auto spin = [&](auto cond) -> bool {
     if (__all_sync(0xffffffffu, cond())) return true;
     unsigned long long t0 = 0;
-    unsigned spins = 0, ns = (unsigned)cfg.need_zfix;   // (field reused by the lean kernels: first back-off, ns)
+    unsigned spins = 0, ns = (unsigned)cfg.spin_ns0;
     while (true) {
       __nanosleep(ns);
       if (__all_sync(0xffffffffu, cond())) return true;
@@ -664,10 +664,10 @@ inline bool lean16_configure_i(const Geom& g, int tile_y_req, int stages_req, in
   cfg->trap_on_timeout = 1;
   // back-off of a waiting warp: first sleep 200 ns, doubling up to 400 (round 2: 20 -> 160 before;
   // cfg2 96.2 -> 97.2 Gcell/s on a slower box, fp16 126.5 -> 129.0: half the polls, less power)
-  cfg->need_zfix = 200;
-  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->need_zfix = atoi(e) < 1 ? 1 : atoi(e);
-  cfg->unroll = 2;                               // (field reused: block order, 2 = stage-major; fp16 cfg2 130.7 -> 131.1)
-  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->unroll = atoi(e) != 0 ? 2 : 1;
+  cfg->spin_ns0 = 200;
+  if (const char* e = getenv("B200FDTD_SPIN_NS0")) cfg->spin_ns0 = atoi(e) < 1 ? 1 : atoi(e);
+  cfg->block_order = 2;                          // stage-major; fp16 cfg2 130.7 -> 131.1
+  if (const char* e = getenv("B200FDTD_LEAN_MAP")) cfg->block_order = atoi(e) != 0 ? 2 : 1;
   int occ = 0;
   const void* fn = lean16_fn<T, LPC>();
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->smem_bytes) !=

@@ -42,14 +42,17 @@ struct SystolicCfg {
   int threads;           // CTA size = roundup32((max tile columns + 2) * Zq)
   int smem_bytes;
   int max_lead;          // a stage may run at most this many planes ahead of the next stage
-  int need_zfix;         // z-columns straddle warps (Zq does not divide 32)
+  union {
+    int need_zfix;       // systolic / systolic_async: z-columns straddle warps (Zq does not divide 32)
+    int spin_ns0;        // systolic_lean: first back-off of a waiting compute warp, ns
+  };
   int trap_on_timeout;
   int pf_ahead;          // systolic_async: planes of L2 prefetch beyond the staging ring
   int svc_sleep_ns;      // systolic_async: back-off of the poller / publisher warps
   int cols;              // systolic_async: adjacent columns per compute thread (1 or 2)
   int spin_ns_max;       // systolic_lean: back-off ceiling of a waiting compute warp
   int discard;           // systolic_lean: drop consumed field lines from L2 (discard.global.L2)
-  int unroll;            // systolic_lean: unroll factor of the plane loop (1 | 2)
+  int block_order;       // systolic_lean: blockIdx -> (stage, tile): 2 = stage-major, 1 = tile-major
   long long l2_window_bytes;
 };
 
