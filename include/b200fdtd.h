@@ -301,7 +301,9 @@ int b200fdtd_session_layout2(const b200fdtd_session* session, int64_t* info);
  *   2. exchange workspace addresses; b200fdtd_session_set_peers(session, low, high)
  *   3. per launch: barrier; b200fdtd_session_slab_reset; barrier; b200fdtd_session_advance.
  *      (The first barrier says every rank has finished its previous launch -- a neighbour still
- *      running would see its mirror slots cleared, or its ghosts overwritten, under its feet.) */
+ *      running would see its mirror slots cleared, or its ghosts overwritten, under its feet.)
+ *      b200fdtd_session_advance returns B200FDTD_EINVAL when no reset ran since the last launch:
+ *      stale counters would make every dependency look met. */
 size_t b200fdtd_session_workspace_bytes_slab(const b200fdtd_desc* desc, int ylo, int yhi);
 int b200fdtd_session_create_slab(const b200fdtd_desc* desc, const void* const* inputs,
                                  void* const* outputs, void* workspace, size_t workspace_bytes,

@@ -900,6 +900,7 @@ struct b200fdtd_session {
   dim3 grid;
   bool slab;            // y-slab session: tiles cover [g.ylo, g.yhi), in-kernel halo exchange
   bool peers_set;
+  bool counters_clear;  // slab: b200fdtd_session_slab_reset ran since the last launch
   SlabPeers peers;
 };
 
@@ -994,7 +995,7 @@ int b200fdtd_session_create_slab(const b200fdtd_desc* desc, const void* const* i
   if (!s) return fail(B200FDTD_EINVAL, "out of host memory");
   s->d = *desc; s->g = g; s->w = w; s->ws = static_cast<char*>(workspace);
   s->plan = plan; s->systolic = systolic;
-  s->slab = slab; s->peers_set = false;
+  s->slab = slab; s->peers_set = false; s->counters_clear = false;
   s->peers.delta_lo = 0; s->peers.delta_hi = 0; s->peers.enabled = slab ? 1 : 0;
   s->reduced = desc->use_reduced_precision != 0;
   s->grid = dim3((g.Y * g.Zq + kTwoPassThreads - 1) / kTwoPassThreads, g.X);
@@ -1050,9 +1051,14 @@ int b200fdtd_session_advance(b200fdtd_session* s, int n0, int nsteps, void* stre
   if (s->slab && !s->peers_set)
     return fail(B200FDTD_EINVAL, "slab session: call b200fdtd_session_set_peers first");
   // A slab's counters (and the mirror slots its neighbours write) are cleared by
-  // b200fdtd_session_slab_reset, between two barriers of the caller -- not here.
+  // b200fdtd_session_slab_reset, between two barriers of the caller -- not here.  A launch over
+  // counters the previous launch left behind would see every dependency as already met.
+  if (s->slab && !s->counters_clear)
+    return fail(B200FDTD_EINVAL, "slab session: call b200fdtd_session_slab_reset (between two "
+                                 "barriers of all ranks) before every advance");
   if (!s->slab)
     CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys), st));
+  s->counters_clear = false;
   unsigned* const sync = reinterpret_cast<unsigned*>(s->ws + s->w.sync);
   int rc;
   if (s->plan.sys.cols == 16)                      // sub-warp variant: fp16 or fp32 storage
@@ -1081,6 +1087,7 @@ int b200fdtd_session_slab_reset(b200fdtd_session* s, void* stream) {
   if (!s->slab) return fail(B200FDTD_EINVAL, "not a y-slab session");
   CUDA_TRY(cudaMemsetAsync(s->ws + s->w.sync, 0, systolic_sync_bytes(s->plan.sys),
                            static_cast<cudaStream_t>(stream)));
+  s->counters_clear = true;
   return B200FDTD_OK;
 }
 

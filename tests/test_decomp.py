@@ -367,7 +367,7 @@ P2P_CASES = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("domain,pml,axis,src_pos,tt", P2P_CASES)
 def test_p2p_slab_wrapping_onto_itself_equals_one_call_engine(built, domain, pml, axis, src_pos, tt):
-  """World 1: the slab's low and high neighbour are the slab itself, so the edge warps store into
+  """World 1: the slab's low and high neighbour are the slab itself, so the couriers store into
   the slab's OWN ghost columns and the edge tiles watch their own mirror slots -- the same code
   path as between two GPUs, minus NVLink.  Must reproduce the periodic one-call engine bit for
   bit (and therefore the C oracle)."""
@@ -399,6 +399,33 @@ def test_p2p_slab_tilings_and_long_run(built):
   for lp in (None, {"tile_y": 5, "stages": 3}, {"tile_y": 13, "stages": 2}, {"tile_y": 1, "stages": 1}):
     got = fdtdz_decomposed_p2p(**{**kw, "launch_params": lp}).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_p2p_slab_chained_launches_and_the_reset_guard(built):
+  """A slab session advances in several launches (the ghosts hold the neighbour's last state), and
+  a launch without b200fdtd_session_slab_reset since the previous one is refused: the counters the
+  previous launch left behind would make every dependency look met."""
+  from pjz_b200 import fdtdz_jax
+  from pjz_b200._decomp import P2PSlabRun
+  from tests.problems import random_problem
+  kw = random_problem(domain=(16, 40, 128), axis=0, pml=(16, 16), tt=61, seed=17, src_pos=5,
+                      output_steps=(9, 61, 7), absorb_pad=4)
+  dev = dict(kw)
+  dev["epsilon"] = torch.from_numpy(kw["epsilon"]).cuda()
+  want = fdtdz_jax.fdtdz(**dev)
+  run = P2PSlabRun(kw)
+  slab = run.slab
+  slab.advance(0, 23)
+  torch.cuda.synchronize()
+  rc = slab.L.b200fdtd_session_advance(slab.session, 23, 10, slab._stream())
+  assert rc != 0 and "slab_reset" in fdtdz_jax._last_error()
+  slab.advance(23, 1)                    # odd and even starting steps, one-step launches
+  slab.advance(24, 12)
+  slab.advance(36, 25)
+  got = run.gathered_snapshots()
+  run.close()
+  assert torch.equal(got, want)
 
 
 def _gpu_worker_p2p(rank, world, port, out_path):
