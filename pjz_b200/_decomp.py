@@ -804,3 +804,25 @@ def fdtdz_decomposed_p2p(epsilon, dt, source_field, source_waveform, source_posi
   out = run.gathered_snapshots() if gather else run.local_snapshots()
   run.close()
   return out
+
+
+def decomposed_engine(kind="p2p", **opts):
+  """An ``engine=`` for ``pjz_b200.field`` / ``scatter`` that solves EVERY engine call on ALL ranks
+  of the process group, the domain cut into slabs (BASELINE.json config 5: domains too large or
+  too slow for one GPU), instead of dealing whole ports to the ranks.
+
+  ``kind``: "p2p" (y-slabs, halo exchange inside the persistent kernel), "y" (y-slabs with ghost
+  zones over NCCL / gloo) or "x" (x-slabs, exchange per half-step).  ``opts`` go to the driver
+  (``group``, ``device``, ``ghost``, ``make_slab``).  The callable is marked ``collective``:
+  ``scatter`` then runs every port on every rank and skips its own broadcast of the fields.
+  """
+  fn = {"p2p": fdtdz_decomposed_p2p, "y": fdtdz_decomposed_y, "x": fdtdz_decomposed}[kind]
+
+  def engine(**kw):
+    if kw.pop("output_projection", None) is not None:
+      raise NotImplementedError("the decomposed engines return snapshots; use fuse_projection=False")
+    return fn(**kw, **opts)
+
+  engine.collective = True
+  engine.__name__ = f"fdtdz_decomposed_{kind}"
+  return engine

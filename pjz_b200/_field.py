@@ -381,7 +381,10 @@ def _scatter_impl(epsilon, omega, modes, betas, pos, is_fwd, sim_params, engine=
   import torch.distributed as dist
   nports = len(modes)
   world, rank = 1, 0
-  if group is not None or (dist.is_available() and dist.is_initialized()):
+  # a ``collective`` engine (pjz_b200._decomp.decomposed_engine) uses all ranks for EACH call: every
+  # rank runs every port and ends up with the whole field, so nothing is dealt or broadcast here
+  collective = bool(getattr(engine, "collective", False))
+  if not collective and (group is not None or (dist.is_available() and dist.is_initialized())):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
   epsilon = _as_tensor(epsilon, dtype=torch.float32)
   mine = [i for i in range(nports) if i % world == rank]

@@ -428,6 +428,28 @@ def test_p2p_slab_chained_launches_and_the_reset_guard(built):
   assert torch.equal(got, want)
 
 
+@pytest.mark.gpu
+def test_field_through_the_decomposed_engine(built):
+  """``pjz_b200.field(engine=decomposed_engine("p2p"))``: the reference-facing call over the
+  y-slab sessions (one rank: the slab wraps onto itself) gives the phasors of the default engine."""
+  from pjz_b200 import SimParams, decomposed_engine, field
+  rng = np.random.default_rng(3)
+  eps = np.ones((3, 24, 32, 20), np.float32)
+  eps[:, :, 10:22, 8:12] = 12.25
+  src = rng.standard_normal((2, 1, 32, 20)).astype(np.float32)
+  omega = np.array([2 * np.pi / 37])
+  p = SimParams(omega_range=(omega[0], omega[0]), tt=120, dt=0.5, absorption_padding=3,
+                absorption_coeff=4e-4, pml_widths=(16, 16), use_reduced_precision=False,
+                domain_zz=128)
+  e = torch.from_numpy(eps).cuda()
+  want = field(e, src, omega, 4, p)
+  got = field(e, src, omega, 4, p, engine=decomposed_engine("p2p"))
+  assert bool(torch.isfinite(want).all()) and float(want.abs().max()) > 0
+  assert torch.equal(got, want)
+  with pytest.raises(NotImplementedError):
+    field(e, src, omega, 4, p, engine=decomposed_engine("p2p"), fuse_projection=True)
+
+
 def _gpu_worker_p2p(rank, world, port, out_path):
   sys.path.insert(0, ROOT)
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

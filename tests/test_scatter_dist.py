@@ -59,6 +59,43 @@ def test_two_rank_scatter_matches_single_process(tmp_path):
       torch.testing.assert_close(got[i][j], want[i][j], rtol=0, atol=0)
 
 
+def _worker_decomposed(rank, world, port, out):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.set_num_threads(1)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from pjz_b200 import decomposed_engine, scatter
+  from tests.test_decomp import OracleSlabY
+  eps, omega, modes, betas, pos, fwd, p = _problem()
+  p = p._replace(tt=60)
+  engine = decomposed_engine("y", ghost=3, make_slab=OracleSlabY)
+  sv = scatter(eps, omega, modes[:2], betas[:2], pos[:2], fwd[:2], p, engine=engine)
+  torch.save([[s.clone() for s in row] for row in sv], out + f".{rank}")
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_scatter_over_a_domain_decomposed_engine(tmp_path):
+  """The second axis of SURVEY.md 8(e) through the reference-facing call: every port is solved by
+  BOTH ranks (y-slabs, ghost zones over gloo, oracle-backed slabs), every rank gets the whole
+  S-matrix, and it equals the single-domain one exactly."""
+  from oracle import fdtd_numpy
+  from pjz_b200 import scatter
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = str(tmp_path / "sv_dd.pt")
+  mp.spawn(_worker_decomposed, args=(2, port, out), nprocs=2, join=True)
+  eps, omega, modes, betas, pos, fwd, p = _problem()
+  p = p._replace(tt=60)
+  want = scatter(eps, omega, modes[:2], betas[:2], pos[:2], fwd[:2], p, engine=fdtd_numpy.fdtdz)
+  for rank in range(2):
+    got = torch.load(out + f".{rank}")
+    for i in range(2):
+      for j in range(2):
+        torch.testing.assert_close(got[i][j], want[i][j], rtol=0, atol=0)
+
+
 def _gpu_worker(rank, world, port, out):
   sys.path.insert(0, ROOT)
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
