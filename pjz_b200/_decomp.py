@@ -800,8 +800,13 @@ def fdtdz_decomposed_p2p(epsilon, dt, source_field, source_waveform, source_posi
             use_reduced_precision=use_reduced_precision, launch_params=launch_params,
             offset=offset)
   run = P2PSlabRun(kw, group=group, device=device)
-  run.run()
-  out = run.gathered_snapshots() if gather else run.local_snapshots()
+  try:
+    run.run()
+    out = run.gathered_snapshots() if gather else run.local_snapshots()
+  except BaseException:
+    if run.world == 1:                   # (with neighbours, close() is collective: a rank that
+      run.close()                        # failed alone must not wait for the others in it)
+    raise
   run.close()
   return out
 
