@@ -169,6 +169,26 @@ def ncu_traffic():
     return None
 
 
+def line_config(name, dims, tt, world, working_set, need_flush):
+  """`config` of the JSON line -- the SAME dict from both arms (the driver compares them): what is
+  run, how it is spread over the devices, and how the L2 is kept cold between timed steps.  What
+  only one arm has (the GPU plan) is a top-level key of that arm's line."""
+  return {"workload": name, "grid": list(dims), "fdtd_steps": tt,
+          "parallelism": "one engine run on one device" if world == 1 else
+          f"port batch: {world} independent engine runs, one per device, no collective",
+          "l2": (f"working set {working_set / 2**20:.0f} MiB: " +
+                 ("smaller than 3x the L2, 512 MiB flush write between timed steps" if need_flush else
+                  "larger than 3x the L2, no flush needed"))}
+
+
+def working_set_bytes(dims, reduced):
+  el = 2 if reduced else 4
+  return dims[0] * dims[1] * dims[2] * (15 * el + 6 * el)
+
+
+B200_L2_BYTES = 126 << 20              # the reference arm has no device to ask
+
+
 def host_threads():
   """All host threads the process may use (torchrun pins OMP_NUM_THREADS=1; ignore that)."""
   try:
@@ -236,7 +256,8 @@ def run_reference(args, rank, world):
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f16-storage/f32-math" if args.reduced else "f32", "data": "synthetic",
-      "config": {"workload": name, "grid": list(dims), "fdtd_steps": tt},
+      "config": line_config(name, dims, tt, world, working_set_bytes(dims, args.reduced),
+                            working_set_bytes(dims, args.reduced) < 3 * B200_L2_BYTES),
       "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port",
                        "sample": sample},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -479,8 +500,7 @@ def main():
   # Cold L2 between timed steps: the default workload's working set (fields x2 + coefficients)
   # is several times the 126 MB L2; smaller workloads get an explicit flush (a 512 MB write)
   # between steps, outside the per-step CUDA events.
-  bytes_per_cell = 15 * (2 if args.reduced else 4) + 6 * (2 if args.reduced else 4)
-  working_set = cells * bytes_per_cell
+  working_set = working_set_bytes(dims, args.reduced)
   l2_bytes = torch.cuda.get_device_properties(local).L2_cache_size
   need_flush = working_set < 3 * l2_bytes
   flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
@@ -651,13 +671,8 @@ def main():
       "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None,
       "dtype": "f16-storage/f32-math" if args.reduced else "f32", "data": "synthetic",
-      "config": {"workload": name, "grid": list(dims), "fdtd_steps": tt,
-                 "parallelism": "single GPU" if world == 1 else
-                 f"port batch: {world} independent engine runs, one per GPU, no collective",
-                 "l2": (f"working set {working_set / 2**20:.0f} MiB vs {l2_bytes / 2**20:.0f} MiB L2: " +
-                        ("512 MiB flush write between timed steps" if need_flush else
-                         "inputs larger than L2, no flush needed")),
-                 "plan": info},
+      "config": line_config(name, dims, tt, world, working_set, need_flush),
+      "plan": info, "l2_bytes": int(l2_bytes),
       "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
       "clocks": clocks, "box": box, "same_box_ab": same_box, "reduced_precision": reduced, "decomp": decomp,
   }

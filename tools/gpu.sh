@@ -20,7 +20,7 @@ for l in sys.stdin:
   if not l.startswith('{'): continue
   j = json.loads(l); r = j.get('roofline') or {}
   print(round(j['value'], 2), j['unit'], 'frac', round(r.get('frac', 0), 3), 'e2e', (j.get('e2e') or {}).get('value'),
-        j['config'].get('plan'), j.get('clocks'), {k: j[k] for k in ('reduced_precision', 'decomp') if k in j})"; }
+        j.get('plan') or j['config'].get('plan'), j.get('clocks'), {k: j[k] for k in ('reduced_precision', 'decomp') if k in j})"; }
 run_one() {
   verb=$1; shift
   case $verb in
