@@ -19,12 +19,14 @@ from tests.systolic_emulator import Emulator
 class SlabEmulator(Emulator):
 
   def __init__(self, kw, world, tiles_per_rank, stages, max_lead=6, need_rule=3, seed=0,
-               courier_war_rule=True, counter_before_data=False):
+               courier_war_rule=True, counter_before_data=False, discard=False,
+               discard_edge_columns=False):
     super().__init__(kw, world * tiles_per_rank, stages, max_lead=max_lead, need_rule=need_rule,
-                     seed=seed)
+                     seed=seed, discard=discard)
     assert self.Y % world == 0 and (self.Y // world) >= tiles_per_rank
     self.W, self.NTr = world, tiles_per_rank
     self.war = courier_war_rule
+    self.discard_edges = discard_edge_columns               # negative control: edge columns too
     self.counter_first = counter_before_data                # negative control: forward, copy later
     self.pending = []                                       # copies owed in that mode
     self.war_would_block = 0                                # times the WAR rule was the binding one
@@ -62,17 +64,31 @@ class SlabEmulator(Emulator):
     Pn = (P + 1) % X
     cy = np.asarray(cols) % Y
     load = np.asarray(list(cols) + [cols[-1] + 1]) % Y
-    ecur = np.stack([E[c][P][load] for c in range(3)])
+    cached = self.discard and a is not None and k >= 0      # E[P] was loaded as "next" last iteration
+    ecur = a["ecache"] if cached else np.stack([E[c][P][load] for c in range(3)])
     enext = np.stack([E[c][Pn][load] for c in range(3)])
     hold = np.stack([H[c][P][cy] for c in range(3)])
     psx, psy = self.psiH[rb][0][P][cy].copy(), self.psiH[rb][1][P][cy].copy()
     if first:                                               # column y0-1 is this rank's LOW ghost
       g = self.glo[r][rb]
-      ecur[:, 0], enext[:, 0], hold[:, 0] = g["E"][:, P], g["E"][:, Pn], g["H"][:, P]
+      if not cached:
+        ecur[:, 0] = g["E"][:, P]
+      enext[:, 0], hold[:, 0] = g["E"][:, Pn], g["H"][:, P]
       psx[0], psy[0] = g["psiH"][0][P], g["psiH"][1][P]
     if last:                                                # column y1 is this rank's HIGH ghost
       g = self.ghi[r][rb]
-      ecur[:, -1], enext[:, -1] = g["E"][:, P], g["E"][:, Pn]
+      if not cached:
+        ecur[:, -1] = g["E"][:, P]
+      enext[:, -1] = g["E"][:, Pn]
+    if self.discard and a is not None:
+      a["ecache"] = enext.copy()
+      if k >= 0:                                            # kernels_lean.cuh: discard.global.L2 of the
+        dead = np.asarray(cols[2:-1]) % Y if len(cols) > 3 else np.asarray([], np.int64)
+        if self.discard_edges:
+          dead = np.asarray(cols[1:]) % Y
+        for c in range(3):                                  # tile's exclusive columns, never the edge
+          E[c][Pn][dead] = np.nan                           # columns a neighbour or a courier reads
+          H[c][P][dead] = np.nan
     ex, ey, ez = ecur[0][:-1], ecur[1][:-1], ecur[2][:-1]
     from oracle import fdtd_numpy as spec
     dzEy, dzEx = spec._dz_fwd(ey), spec._dz_fwd(ex)

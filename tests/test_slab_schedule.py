@@ -22,6 +22,31 @@ def test_slab_schedule_is_exact_under_random_interleaving(world, tiles, stages, 
   np.testing.assert_array_equal(out, ref)
 
 
+@pytest.mark.parametrize("world,tiles,stages,axis,seed", [(2, 1, 4, 0, 0), (2, 2, 3, 1, 1), (1, 1, 5, 2, 2),
+                                                        (4, 1, 2, 2, 3)])
+def test_l2_discard_never_hits_a_line_a_courier_or_a_ghost_reader_needs(world, tiles, stages, axis, seed):
+  """With the consumed lines of a tile's exclusive columns poisoned (discard.global.L2), a slab
+  run is still exact: couriers read edge columns only, and those are never discarded."""
+  kw = random_problem(domain=(9, 16, 8), axis=axis, tt=11, seed=seed, output_steps=(3, 11, 2))
+  ref = fdtd_numpy.fdtdz(**kw)
+  out = SlabEmulator(kw, world, tiles, stages, max_lead=4, seed=seed, discard=True).run()
+  assert np.isfinite(out).all()
+  np.testing.assert_array_equal(out, ref)
+
+
+def test_discarding_the_edge_columns_is_detected():
+  """Negative control: were the tile-edge columns discarded too, a neighbour tile's halo load or a
+  courier would pick up a poisoned line."""
+  kw = random_problem(domain=(9, 16, 8), axis=0, tt=11, seed=0, output_steps=(3, 11, 2))
+  ref = fdtd_numpy.fdtdz(**kw)
+  wrong = 0
+  for seed in range(3):
+    out = SlabEmulator(kw, 2, 1, 4, max_lead=4, seed=seed, discard=True,
+                       discard_edge_columns=True).run()
+    wrong += not np.array_equal(out, ref)
+  assert wrong >= 1
+
+
 def test_couriers_may_lag_arbitrarily():
   """A courier that is scheduled rarely (here: 20x less often than a tile) delays its neighbour
   but never corrupts it."""
