@@ -85,6 +85,19 @@ def _is_torch(a):
   return type(a).__module__.split(".")[0] == "torch"
 
 
+def _adopt(a):
+  """Foreign device arrays (JAX, CuPy, ... -- anything with ``__dlpack__`` that is neither a torch
+  tensor nor a NumPy array) enter zero-copy through DLPack; everything else is returned as is.
+  Returns ``(array, adopted)``."""
+  if a is None or _is_torch(a) or isinstance(a, np.ndarray) or not hasattr(a, "__dlpack__"):
+    return a, False
+  import torch
+  try:
+    return torch.from_dlpack(a), True
+  except Exception:                                          # noqa: BLE001
+    return a, False                                          # the array interface (host path) still works
+
+
 def _shape(a):
   return tuple(int(s) for s in a.shape)
 
@@ -175,6 +188,21 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
   fuses the frequency projection of /root/reference/src/pjz/_field.py:272-279 into the time
   stepping: the result is ``(rows, 3, xx, yy, zz)`` with ``out[r] = sum_s W[r, s] * snapshot_s``
   and no snapshot is written."""
+  foreign = None                                             # e.g. "jax": results go back the same way
+  adopted = []
+  for a in (epsilon, source_field, source_waveform, absorption_mask, pml_kappa, pml_sigma,
+            pml_alpha, output_projection):
+    t, was = _adopt(a)
+    if was and foreign is None:
+      foreign = type(a).__module__.split(".")[0]
+    adopted.append(t)
+  (epsilon, source_field, source_waveform, absorption_mask, pml_kappa, pml_sigma, pml_alpha,
+   output_projection) = adopted
+  if foreign is not None:
+    return _return_as(foreign, fdtdz(
+        epsilon, dt, source_field, source_waveform, source_position, absorption_mask, pml_kappa,
+        pml_sigma, pml_alpha, pml_widths, output_steps, use_reduced_precision, launch_params,
+        offset, output_projection=output_projection))
   arrays = [epsilon, source_field, source_waveform, absorption_mask, pml_kappa, pml_sigma,
             pml_alpha]
   if output_projection is not None:
@@ -225,6 +253,19 @@ def fdtdz(epsilon, dt, source_field, source_waveform, source_position, absorptio
       raise RuntimeError(f"b200fdtd_run failed ({rc}): {_last_error()}")
     # ws/dev are released to torch's caching allocator, which is stream-ordered.
     return out
+
+
+def _return_as(foreign, out):
+  """Hand the result back to the framework the DLPack inputs came from (JAX: ``jax.dlpack``,
+  zero-copy); anything else gets the torch tensor / NumPy array, both of which speak DLPack."""
+  if foreign in ("jax", "jaxlib"):
+    try:
+      import jax.dlpack
+      import torch
+      return jax.dlpack.from_dlpack(out if _is_torch(out) else torch.from_numpy(out))
+    except ImportError:
+      pass
+  return out
 
 
 def adjoint_reduce(fields, coef):

@@ -139,3 +139,42 @@ def test_install_registers_module_name():
   import fdtdz_jax as shim  # the name pjz imports (/root/reference/src/pjz/_field.py:6)
   assert shim.fdtdz is fdtdz_jax.fdtdz
   del sys.modules["fdtdz_jax"]
+
+
+def test_foreign_device_arrays_are_adopted_through_dlpack():
+  """Anything that speaks DLPack and is neither torch nor NumPy (JAX, CuPy) enters zero-copy;
+  torch tensors, NumPy arrays, lists and None pass through untouched."""
+  import torch
+  from pjz_b200 import fdtdz_jax
+
+  class Foreign:                                  # stands in for a jax.Array
+    def __init__(self, t):
+      self._t = t
+      self.shape = tuple(t.shape)
+
+    def __dlpack__(self, *a, **k):
+      return self._t.__dlpack__(*a, **k)
+
+    def __dlpack_device__(self):
+      return self._t.__dlpack_device__()
+
+  t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+  got, was = fdtdz_jax._adopt(Foreign(t))
+  assert was and isinstance(got, torch.Tensor) and got.data_ptr() == t.data_ptr()
+  assert torch.equal(got, t)
+  for same in (t, t.numpy(), [1.0, 2.0], None):
+    got, was = fdtdz_jax._adopt(same)
+    assert got is same and not was
+
+  class Broken:
+    shape = (1,)
+
+    def __dlpack__(self, *a, **k):
+      raise TypeError("no")
+
+    def __dlpack_device__(self):
+      return (1, 0)
+  b = Broken()
+  got, was = fdtdz_jax._adopt(b)
+  assert got is b and not was
+  assert fdtdz_jax._return_as("cupy", t) is t
